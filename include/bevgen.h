@@ -1,0 +1,147 @@
+/*
+ * bevgen.h -- C ABI of libbevgen_b200.so: B200 (sm_100a) BEV input generation.
+ *
+ * Drop-in boundary for the ONE hot path of Nadeem202020/VisionTransformer-Intention-Prediction:
+ * the BEV input generation its Dataset does per sample in CPU numpy/OpenCV.  The reference
+ * has no FFI of its own: its boundary is the set of Python names dataset.py:21-23 imports
+ * from utils.py and calls at dataset.py:340,347,348,353.  Each entry point below names the
+ * reference function (file:line, relative to the reference repo) whose arithmetic it
+ * replaces; the Python host layer (bev_ops.py) keeps the reference's names and signatures
+ * on top of these calls, and INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller unless the parameter is
+ *     documented as "host"; nothing here allocates device memory
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*)
+ *   - return value: 0 = ok, > 0 = cudaError_t from a launch, < 0 = BEVGEN_E_* below
+ *   - grids are float32, C-contiguous [C,400,720] per frame, frames stacked [B,C,400,720]
+ *     (the layout dataset.py:146-147 stacks and train_vit.py:159 feeds to the model)
+ */
+#ifndef BEVGEN_H_
+#define BEVGEN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEVGEN_ABI_VERSION 1
+
+/* grid constants (reference constants.py:28-47) */
+#define BEVGEN_GRID_H 400
+#define BEVGEN_GRID_W 720
+#define BEVGEN_ZBINS 29
+#define BEVGEN_MAP_CHANNELS 9
+#define BEVGEN_MAX_DROP_RECTS 5      /* utils.py:485 num_patches_range = (1, 5) */
+#define BEVGEN_MAX_POLYLINE_VERTS 1024
+
+#define BEVGEN_E_INVALID_ARG (-1)
+#define BEVGEN_E_WORKSPACE   (-2)
+#define BEVGEN_E_UNSUPPORTED (-3)
+
+typedef void *bevgen_stream_t;       /* cudaStream_t */
+
+int bevgen_abi_version(void);
+/* out[10] (host) = GRID_H, GRID_W, VOXEL, OFF_X, OFF_Y, Z_MIN, Z_MAX, ZBINS, MAP_CH, Z_MAX-Z_MIN */
+void bevgen_constants(double *out);
+const char *bevgen_error_string(int code);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t bevgen_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * transform_points -- utils.py:27-33.  out[i,:] = (T . [x y z 1]^T)[:3] in float64, FMA chain
+ * in k order (what numpy's dgemm does).  T is a HOST pointer to 16 doubles (row-major 4x4).
+ * `stride` = elements per input row (>= 3).  out is float64 [n,3].
+ * ------------------------------------------------------------------------------------- */
+int bevgen_transform_points_f32(const float *pts, int64_t n, int64_t stride, const double *T_host,
+                                double *out, bevgen_stream_t stream);
+int bevgen_transform_points_f64(const double *pts, int64_t n, int64_t stride, const double *T_host,
+                                double *out, bevgen_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * create_intentnet_lidar_bev -- utils.py:62-106 (and, for the fused form, the per-sweep
+ * transform of dataset.py:339-340 in front of it).
+ *
+ * Frames b = 0..B-1, sweep slots s = 0..S-1 (oldest first); sweep (b,s) owns the point rows
+ * [sweep_offsets[b*S+s], sweep_offsets[b*S+s+1]).  An empty range is the reference's
+ * `None` / missing sweep: its 29 channels stay zero (utils.py:75-76).  Output channel =
+ * s*29 + z_bin (utils.py:97,102); out is [B, S*29, 400, 720] and is fully written (zero
+ * fill included -- the caller does not pre-clear it).
+ *
+ *   fused:   pts4   float32 [N,4] = x,y,z,intensity in the SWEEP frame
+ *            rel_tf float64 [B*S,16] = ego_SE3_world @ sweep_SE3 (dataset.py:339), device
+ *   ego_f64: pts3   float64 [N,3] already in the ego frame (what dataset.py:340 produces)
+ *            intensity float32 [N]
+ *
+ * Optional train-time fusions (NULL = off), exact by construction:
+ *   flip        uint8 [B]   1 = mirror W (utils.py:399)
+ *   drop_rects  int32 [B, 5, 4] = (y0, x0, ph, pw); drop_counts int32 [B] (utils.py:496)
+ *               -- only meaningful when no rotate/scale follows for that frame
+ *
+ * max_sweep_points: max over sweeps of the row count (host knows it; sizes the grid).
+ * algo: 0 = tiled (bin by row, shared-memory tile, TMA bulk store)   [default]
+ *       1 = atomic (memset + global atomicMax)                        [cross-check / fallback]
+ * ------------------------------------------------------------------------------------- */
+size_t bevgen_lidar_workspace_bytes(int64_t total_points, int B, int S);
+
+int bevgen_lidar_bev_fused(const float *pts4, const int32_t *sweep_offsets, const double *rel_tf,
+                           int B, int S, int64_t total_points, int max_sweep_points,
+                           const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,
+                           float *out, void *workspace, size_t workspace_bytes, int algo,
+                           bevgen_stream_t stream);
+
+int bevgen_lidar_bev_ego_f64(const double *pts3, const float *intensity, const int32_t *sweep_offsets,
+                             int B, int S, int64_t total_points, int max_sweep_points,
+                             const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,
+                             float *out, void *workspace, size_t workspace_bytes, int algo,
+                             bevgen_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * rasterize_map_ego_centric -- utils.py:108-182 (with world_to_bev_pixel utils.py:47-60,
+ * cv2.fillPoly / cv2.polylines utils.py:155-180) on pre-parsed maps.
+ *
+ * Map table (device, may hold several maps back to back; see maps.py for the layout):
+ *   verts  float64 [V,2]; pl_off int32 [P+1]; lanes int32 [L,4] (left pl, right pl, flags, 0);
+ *   cws int32 [CW]
+ * frame_map int32 [B,4] = lane_begin, lane_count, cw_begin, cw_count (rows into lanes / cws)
+ * ego_T     float64 [B,9] = 3x3 world->ego matrix of utils.py:35-45 per frame
+ * max_prims = max over frames of lane_count + cw_count
+ * out float32 [B,9,400,720], fully written.  flip / drop_* as above.
+ * ------------------------------------------------------------------------------------- */
+size_t bevgen_map_workspace_bytes(int B);
+
+int bevgen_map_raster(const double *verts, const int32_t *pl_off, const int32_t *lanes,
+                      const int32_t *cws, const int32_t *frame_map, const double *ego_T,
+                      int B, int max_prims,
+                      const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,
+                      float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
+
+/* world_to_bev_pixel -- utils.py:47-60: xy float64 [m,2] -> int64 [m,2] (px,py); T_host 9 doubles */
+int bevgen_world_to_bev_pixel(const double *xy, int64_t m, const double *T_host, int64_t *out,
+                              bevgen_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Augmentation -- utils.py:394-498, image part (GT-box arithmetic stays on the host).
+ * Per-frame parameters live in a device array of bevgen_aug_params, drawn on the host in the
+ * reference's RNG order (utils.py:398,421-422,455-456,488-494).
+ *   src, dst: [B, C, 400, 720]; dst != src.  Order: flip -> rotate -> scale -> dropout
+ *   (utils.py:508-511).  One fused gather per output pixel reproduces the reference's
+ *   intermediate float32 roundings exactly (rotate: cv2.warpAffine fixed-point bilinear,
+ *   utils.py:430-433; scale: cv2.resize separable bilinear, utils.py:462).
+ * ------------------------------------------------------------------------------------- */
+typedef struct bevgen_aug_params {
+    double minv[6];        /* inverted 2x3 of cv2.getRotationMatrix2D (dst->src), used if do_rotate */
+    double scale;          /* s of utils.py:456, used if do_scale */
+    int32_t do_flip, do_rotate, do_scale, n_rects;
+    int32_t rects[BEVGEN_MAX_DROP_RECTS * 4];   /* y0, x0, ph, pw */
+} bevgen_aug_params;
+
+int bevgen_augment(const float *src, float *dst, int B, int C, const bevgen_aug_params *params,
+                   bevgen_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVGEN_H_ */

@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's BEV-generation functions on top of the C ABI.
+
+Two layers, both thin (PyTorch is used for device memory and streams only):
+
+* the reference's Dataset-facing names with identical signatures and return types
+  (numpy in -> numpy out), so ``dataset.py`` can rebind them unchanged:
+    ``transform_points``              utils.py:27-33
+    ``create_intentnet_lidar_bev``    utils.py:62-106
+    ``rasterize_map_ego_centric``     utils.py:108-182      (map_ops.py)
+    ``augment_bev`` / ``random_*``    utils.py:394-517      (augment.py)
+* the batched, device-resident fast path (``lidar_bev_from_sweeps`` ...) that replaces
+  transform + scatter for a whole batch of frames in four kernel launches and writes the
+  ``[B, 290, 400, 720]`` tensor the models consume (dataset.py:146-147, train_vit.py:154-159).
+
+No CPU fallback: every function here ends in a call into ``libbevgen_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LIDAR_SWEEPS)
+
+ALGO_TILED, ALGO_ATOMIC = 0, 1
+MAX_DROP_RECTS = 5
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("bevgen_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _dev(a, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    """numpy / tensor -> contiguous device tensor of `dtype` (no copy when already right)."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device, non_blocking=True)
+
+
+class _Workspace:
+    """Grow-only scratch buffer per (device, purpose); kernels never allocate."""
+
+    def __init__(self) -> None:
+        self._bufs = {}
+
+    def get(self, key, nbytes: int, device: torch.device) -> torch.Tensor:
+        buf = self._bufs.get((key, device))
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+            self._bufs[(key, device)] = buf
+        return buf
+
+    def clear(self) -> None:
+        self._bufs.clear()
+
+
+workspace = _Workspace()
+
+
+def _aug_fusion_args(B, flip, drop_rects, drop_counts, device):
+    f = None if flip is None else _dev(flip, torch.uint8, device).reshape(B)
+    if (drop_rects is None) != (drop_counts is None):
+        raise ValueError("drop_rects and drop_counts go together")
+    r = c = None
+    if drop_rects is not None:
+        r = _dev(drop_rects, torch.int32, device).reshape(B, MAX_DROP_RECTS, 4)
+        c = _dev(drop_counts, torch.int32, device).reshape(B)
+    return f, r, c
+
+
+# =========================================================================== batched fast path
+def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_sweeps: int = LIDAR_SWEEPS, *,
+                          max_sweep_points: Optional[int] = None, flip=None, drop_rects=None, drop_counts=None,
+                          out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
+    """Fused dataset.py:339-340 + utils.py:62-106 for ``num_frames`` frames.
+
+    points4        float32 [N,4]  (x, y, z, intensity) in each sweep's own frame, sweeps concatenated
+    sweep_offsets  int32 [B*S+1]  CSR offsets; an empty range = missing sweep (its 29 channels stay 0)
+    rel_tf         float64 [B*S,4,4]  ego_SE3_world @ sweep_SE3 (pose.sweep_rel_transforms)
+    returns        float32 CUDA tensor [B, S*29, 400, 720]
+    """
+    device = _require_cuda()
+    B, S = int(num_frames), int(num_sweeps)
+    host_off = None
+    if not isinstance(sweep_offsets, torch.Tensor):
+        host_off = np.ascontiguousarray(sweep_offsets, dtype=np.int32)
+    pts = _dev(points4, torch.float32, device)
+    off = _dev(sweep_offsets, torch.int32, device)
+    tf = _dev(rel_tf, torch.float64, device).reshape(-1, 16)
+    if pts.dim() != 2 or pts.shape[1] != 4:
+        raise ValueError("points4 must be [N,4] float32 (x,y,z,intensity)")
+    if off.numel() != B * S + 1 or tf.shape[0] != B * S:
+        raise ValueError("sweep_offsets must have B*S+1 entries and rel_tf B*S matrices")
+    n = int(pts.shape[0])
+    if max_sweep_points is None:
+        if host_off is None:
+            host_off = off.cpu().numpy()
+        max_sweep_points = int(np.diff(host_off).max()) if B * S else 0
+    f, r, c = _aug_fusion_args(B, flip, drop_rects, drop_counts, device)
+    shape = (B, S * LIDAR_HEIGHT_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
+    L = _native.lib()
+    ws = None
+    wbytes = 0
+    if algo == ALGO_TILED:
+        wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
+        ws = workspace.get("lidar", wbytes, device)
+    rc = L.bevgen_lidar_bev_fused(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
+                                  _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
+    _native.check(rc, "bevgen_lidar_bev_fused")
+    return out
+
+
+def lidar_bev_from_ego_points(points3, intensity, sweep_offsets, num_frames: int, num_sweeps: int = LIDAR_SWEEPS, *,
+                              max_sweep_points: Optional[int] = None, flip=None, drop_rects=None, drop_counts=None,
+                              out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
+    """utils.py:62-106 on float64 points that are already in the ego frame (batched)."""
+    device = _require_cuda()
+    B, S = int(num_frames), int(num_sweeps)
+    host_off = None if isinstance(sweep_offsets, torch.Tensor) else np.ascontiguousarray(sweep_offsets, dtype=np.int32)
+    pts = _dev(points3, torch.float64, device)
+    inten = _dev(intensity, torch.float32, device)
+    off = _dev(sweep_offsets, torch.int32, device)
+    if pts.dim() != 2 or pts.shape[1] != 3 or inten.numel() != pts.shape[0] or off.numel() != B * S + 1:
+        raise ValueError("points3 [N,3] float64, intensity [N] float32, sweep_offsets [B*S+1] expected")
+    n = int(pts.shape[0])
+    if max_sweep_points is None:
+        if host_off is None:
+            host_off = off.cpu().numpy()
+        max_sweep_points = int(np.diff(host_off).max()) if B * S else 0
+    f, r, c = _aug_fusion_args(B, flip, drop_rects, drop_counts, device)
+    shape = (B, S * LIDAR_HEIGHT_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
+    L = _native.lib()
+    ws, wbytes = None, 0
+    if algo == ALGO_TILED:
+        wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
+        ws = workspace.get("lidar", wbytes, device)
+    rc = L.bevgen_lidar_bev_ego_f64(_ptr(pts), _ptr(inten), _ptr(off), B, S, n, int(max_sweep_points),
+                                    _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
+    _native.check(rc, "bevgen_lidar_bev_ego_f64")
+    return out
+
+
+# =========================================================================== reference signatures
+def transform_points(points: np.ndarray, transform_matrix: np.ndarray) -> np.ndarray:
+    """Drop-in for utils.py:27-33: float64 (N,3) = (T @ [x y z 1]^T)^T[:, :3] computed on the GPU.
+
+    Empty input returns ``np.empty((0, 3), dtype=points.dtype)`` exactly as utils.py:29-30."""
+    points = np.asarray(points)
+    if points.shape[0] == 0:
+        return np.empty((0, 3), dtype=points.dtype)
+    if points.ndim != 2 or points.shape[1] < 3:
+        raise ValueError("points must be (N, >=3)")
+    device = _require_cuda()
+    T = np.ascontiguousarray(transform_matrix, dtype=np.float64)
+    if T.shape != (4, 4):
+        raise ValueError("transform_matrix must be 4x4")
+    n = points.shape[0]
+    out = torch.empty((n, 3), dtype=torch.float64, device=device)
+    L = _native.lib()
+    if points.dtype == np.float64:
+        p = _dev(points[:, :3], torch.float64, device)
+        rc = L.bevgen_transform_points_f64(_ptr(p), n, 3, C.c_void_p(T.ctypes.data), _ptr(out), _stream_ptr())
+    else:   # float16 / float32 / ints widen exactly to float64 through float32 only if they fit; be exact:
+        if points.dtype in (np.float16, np.float32):
+            p = _dev(points[:, :3].astype(np.float32, copy=False), torch.float32, device)
+            rc = L.bevgen_transform_points_f32(_ptr(p), n, 3, C.c_void_p(T.ctypes.data), _ptr(out), _stream_ptr())
+        else:
+            p = _dev(points[:, :3].astype(np.float64), torch.float64, device)
+            rc = L.bevgen_transform_points_f64(_ptr(p), n, 3, C.c_void_p(T.ctypes.data), _ptr(out), _stream_ptr())
+    _native.check(rc, "bevgen_transform_points")
+    return out.cpu().numpy()
+
+
+def _pack_sweeps(points_list: Sequence, intensity_list: Sequence, num_expected_sweeps: int):
+    """Concatenate the reference's list-of-arrays form into (points float64 [N,3], intensity float32 [N],
+    offsets int32 [S+1]); applies the reference's skip rules (utils.py:71-76)."""
+    loaded = min(len(points_list), len(intensity_list))
+    P, I = [], []
+    counts = np.zeros(num_expected_sweeps, np.int64)
+    for s in range(loaded):
+        pts, inten = points_list[s], intensity_list[s]
+        if pts is None or inten is None or pts.shape[0] == 0:
+            continue
+        if s >= num_expected_sweeps:
+            # the reference indexes bev[channel_offset + h] out of range here (utils.py:102)
+            raise IndexError(f"index {s * LIDAR_HEIGHT_CHANNELS} is out of bounds for axis 0 with size "
+                             f"{num_expected_sweeps * LIDAR_HEIGHT_CHANNELS}")
+        pts = np.asarray(pts)
+        inten = np.asarray(inten)
+        if inten.shape[0] != pts.shape[0]:
+            raise IndexError("boolean index did not match: points and intensity lengths differ")
+        P.append(np.ascontiguousarray(pts[:, :3], dtype=np.float64))
+        I.append(np.ascontiguousarray(inten, dtype=np.float32))
+        counts[s] = pts.shape[0]
+    off = np.zeros(num_expected_sweeps + 1, np.int32)
+    off[1:] = np.cumsum(counts)
+    pts_all = np.concatenate(P, 0) if P else np.zeros((0, 3), np.float64)
+    int_all = np.concatenate(I, 0) if I else np.zeros((0,), np.float32)
+    return pts_all, int_all, off
+
+
+def create_intentnet_lidar_bev(points_list, intensity_list, num_expected_sweeps: int = LIDAR_SWEEPS, *,
+                               as_tensor: bool = False, algo: int = ALGO_TILED):
+    """Drop-in for utils.py:62-106.
+
+    points_list[s]   (N_s, >=3) points already in the current ego frame (float64 on the Dataset
+                     path, dataset.py:340) or None;  intensity_list[s]  (N_s,) or None.
+    Returns float32 ``[29*num_expected_sweeps, 400, 720]`` -- a fresh numpy array like the
+    reference, or the CUDA tensor when ``as_tensor=True`` (skips the 334 MB device->host copy).
+    Parity domain: float64 points (other dtypes are widened to float64 first), intensities
+    finite or +inf and >= 0.
+    """
+    pts, inten, off = _pack_sweeps(points_list, intensity_list, num_expected_sweeps)
+    out = lidar_bev_from_ego_points(pts, inten, off, 1, num_expected_sweeps, algo=algo)[0]
+    return out if as_tensor else out.cpu().numpy()

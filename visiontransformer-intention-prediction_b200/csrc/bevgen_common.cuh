@@ -1,0 +1,113 @@
+// bevgen_common.cuh -- shared constants, exact-arithmetic device helpers, PTX wrappers (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bevgen.h"
+
+namespace bevgen {
+
+// ---- grid constants: reference constants.py:28-47 ------------------------------------------
+constexpr int kH = BEVGEN_GRID_H;          // 400 rows   (ego x: +60 m at row 0 ... -20 m)
+constexpr int kW = BEVGEN_GRID_W;          // 720 cols   (ego y: -72 m ... +72 m)
+constexpr int kZ = BEVGEN_ZBINS;           // 29 height bins per sweep
+constexpr int kMapC = BEVGEN_MAP_CHANNELS; // 9
+constexpr double kVoxel = 0.2;
+constexpr double kOffX = 360.0;            // BEV_PIXEL_OFFSET_X
+constexpr double kOffY = 300.0;            // BEV_PIXEL_OFFSET_Y
+constexpr double kZMin = -2.0;
+constexpr double kZMax = 3.8;
+constexpr double kZSpan = kZMax - kZMin;   // folded in IEEE double exactly like Python's 3.8-(-2.0)
+constexpr int kPlane = kH * kW;            // 288 000
+constexpr int kRowTileElems = kZ * kW;     // one (sweep,row) tile: 29 x 720 floats = 83 520 B
+constexpr int kMaxRects = BEVGEN_MAX_DROP_RECTS;
+
+extern long long g_launch_count;           // host-side counter (cabi.cu)
+
+#define BEVGEN_CHECK_LAUNCH()                                  \
+    do {                                                       \
+        ++::bevgen::g_launch_count;                            \
+        cudaError_t e__ = cudaGetLastError();                  \
+        if (e__ != cudaSuccess) return (int)e__;               \
+    } while (0)
+
+#define BEVGEN_CUDA(call)                                      \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return (int)e__;               \
+    } while (0)
+
+// ---- exact arithmetic ------------------------------------------------------------------------
+// All binning math uses the round-to-nearest intrinsics so that neither -fmad nor any other
+// contraction can change a bit; the only fused operations are the explicit __fma_rn chains that
+// restate OpenBLAS's dgemm accumulation.
+
+struct Pose34 { double m[12]; };   // rows 0..2 of the 4x4 rel_tf (row 3 is 0 0 0 1)
+
+__device__ __forceinline__ void xform_point(const double* __restrict__ T, double x, double y, double z,
+                                            double& ox, double& oy, double& oz) {
+    // utils.py:32: (T @ [x y z 1]^T), per row: fma chain k = 0..3 starting from +0.0
+    ox = __fma_rn(T[3], 1.0, __fma_rn(T[2], z, __fma_rn(T[1], y, __fma_rn(T[0], x, 0.0))));
+    oy = __fma_rn(T[7], 1.0, __fma_rn(T[6], z, __fma_rn(T[5], y, __fma_rn(T[4], x, 0.0))));
+    oz = __fma_rn(T[11], 1.0, __fma_rn(T[10], z, __fma_rn(T[9], y, __fma_rn(T[8], x, 0.0))));
+}
+
+// utils.py:80-95.  Returns false when the point is masked out (utils.py:83-87).
+__device__ __forceinline__ bool lidar_voxel(double x, double y, double z, int& py, int& px, int& zb) {
+    const double fx = floor(__dadd_rn(kOffX, __ddiv_rn(y, kVoxel)));   // utils.py:80
+    const double fy = floor(__dsub_rn(kOffY, __ddiv_rn(x, kVoxel)));   // utils.py:81
+    // NaN / +-inf / out-of-range fail these compares, as the reference's INT_MIN cast does
+    if (!(fx >= 0.0 && fx < (double)kW && fy >= 0.0 && fy < (double)kH && z >= kZMin && z < kZMax)) return false;
+    const double fz = floor(__dmul_rn(__ddiv_rn(__dsub_rn(z, kZMin), kZSpan), (double)kZ));   // utils.py:94
+    int b = (int)fz;
+    b = b < 0 ? 0 : (b > kZ - 1 ? kZ - 1 : b);                                                // utils.py:95
+    px = (int)fx; py = (int)fy; zb = b;
+    return true;
+}
+
+// utils.py:52-60 for one map vertex; T = 3x3 row-major.  Returns rounded (half-even) pixel coords as
+// doubles-turned-int64 semantics: values outside int32 are clamped far outside the grid.
+__device__ __forceinline__ void map_vertex_px(const double* __restrict__ T, double wx, double wy,
+                                              long long& px, long long& py) {
+    const double ex = __fma_rn(T[2], 1.0, __fma_rn(T[1], wy, __fma_rn(T[0], wx, 0.0)));
+    const double ey = __fma_rn(T[5], 1.0, __fma_rn(T[4], wy, __fma_rn(T[3], wx, 0.0)));
+    const double rx = rint(__dadd_rn(kOffX, __ddiv_rn(ey, kVoxel)));   // np.round = half-to-even
+    const double ry = rint(__dsub_rn(kOffY, __ddiv_rn(ex, kVoxel)));
+    // astype(int): out-of-range / NaN -> INT64_MIN (x86 cvttsd2si)
+    px = (rx >= -9223372036854775808.0 && rx < 9223372036854775808.0) ? (long long)rx : (long long)0x8000000000000000LL;
+    py = (ry >= -9223372036854775808.0 && ry < 9223372036854775808.0) ? (long long)ry : (long long)0x8000000000000000LL;
+}
+
+// per-frame dropout rectangles, (y0, x0, ph, pw) as drawn by utils.py:490-494
+__device__ __forceinline__ bool in_rects(const int* __restrict__ r, int n, int y, int x) {
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < kMaxRects; ++k) {
+        if (k < n) {
+            const int y0 = r[4 * k], x0 = r[4 * k + 1];
+            hit |= (y >= y0) & (y < y0 + r[4 * k + 2]) & (x >= x0) & (x < x0 + r[4 * k + 3]);
+        }
+    }
+    return hit;
+}
+
+// ---- PTX wrappers: bulk async copy (TMA, non-tensor form) -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared::cta -> global, completion tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {   // <= N groups may still be READING their smem source
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
+// order this thread's generic-proxy smem writes before later async-proxy (TMA) reads
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace bevgen

@@ -1,0 +1,380 @@
+// lidar.cu -- multi-sweep LiDAR aggregation -> height-binned max-intensity BEV grid (sm_100a).
+//
+// Replaces, for a whole batch of frames in four launches:
+//   transform_points            reference utils.py:27-33   (per sweep, dataset.py:339-340)
+//   create_intentnet_lidar_bev  reference utils.py:62-106
+//
+// Data flow (HBM):   points [N,4] f32 --K_bin_count--> tmp records [N] u64 + row histogram
+//                    --K_bin_scan--> row-bin starts --K_bin_scatter--> records sorted by (frame,sweep,row)
+//                    --K_raster_store--> out [B, S*29, 400, 720] f32 (every byte written exactly once)
+//
+// A "tile" is one (frame, sweep, row): 29 height channels x 720 columns = 83 520 B.  The raster kernel
+// keeps two such tiles in shared memory per SM, applies the tile's records with warp-aggregated
+// (__match_any_sync) shared-memory atomicMax, and flushes the tile with 29 TMA bulk stores
+// (cp.async.bulk.global.shared::cta, 2 880 B each = one channel row).  Zero fill is the untouched part
+// of the tile, so no memset pass and no read-modify-write of the 334 MB/frame output ever happens.
+#include "bevgen_common.cuh"
+
+namespace bevgen {
+
+namespace {
+
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+constexpr int kBinThreads = 256;
+constexpr int kBinItems = 4;
+constexpr int kBinChunk = kBinThreads * kBinItems;     // points per CTA in the two binning passes
+constexpr int kRasterThreads = 256;
+constexpr int kTileBytes = kRowTileElems * 4;          // 83 520
+constexpr int kRowBytes = kW * 4;                      // 2 880 (multiple of 16: bulk-copy legal)
+
+struct LidarIn {
+    const float4* pts4;        // MODE 0
+    const double* rel_tf;      // MODE 0: [B*S,16]
+    const double* pts3;        // MODE 1
+    const float* intensity;    // MODE 1
+    const int32_t* sweep_off;  // [B*S+1]
+    const uint8_t* flip;       // [B] or null
+    const int32_t* rects;      // [B,5,4] or null
+    const int32_t* nrects;     // [B] or null
+    int S;
+};
+
+// One point -> (row, cell-in-row-tile, intensity bits) or invalid.  MODE 0 transforms first.
+template <int MODE>
+__device__ __forceinline__ bool point_record(const LidarIn& in, long long i, const double* sT, bool flip,
+                                             const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits) {
+    double x, y, z;
+    float v;
+    if (MODE == 0) {
+        const float4 p = __ldcs(in.pts4 + i);             // streaming 16 B load, fully coalesced
+        xform_point(sT, (double)p.x, (double)p.y, (double)p.z, x, y, z);
+        v = p.w;
+    } else {
+        x = __ldcs(in.pts3 + 3 * i); y = __ldcs(in.pts3 + 3 * i + 1); z = __ldcs(in.pts3 + 3 * i + 2);
+        v = __ldcs(in.intensity + i);
+    }
+    int py, px, zb;
+    if (!lidar_voxel(x, y, z, py, px, zb)) return false;
+    // max with the +0.0 initial grid: only strictly positive intensities can change a voxel
+    // (documented domain: finite or +inf, >= 0; then float max == unsigned max on the bit pattern)
+    if (!(v > 0.0f)) return false;
+    if (flip) px = kW - 1 - px;                           // utils.py:399 fused
+    if (nrect && in_rects(sRect, nrect, py, px)) return false;   // utils.py:496 fused
+    row = py;
+    cell = (uint32_t)(zb * kW + px);
+    bits = __float_as_uint(v);
+    return true;
+}
+
+__device__ __forceinline__ void load_frame_consts(const LidarIn& in, int bs, int b, int mode, double* sT, int* sRect,
+                                                  int& nrect, bool& flip) {
+    if (mode == 0 && threadIdx.x < 12) sT[threadIdx.x] = in.rel_tf[(size_t)bs * 16 + threadIdx.x];
+    nrect = in.nrects ? in.nrects[b] : 0;
+    nrect = nrect > kMaxRects ? kMaxRects : nrect;
+    if ((int)threadIdx.x < 4 * nrect) sRect[threadIdx.x] = in.rects[(size_t)b * kMaxRects * 4 + threadIdx.x];
+    flip = in.flip ? (in.flip[b] != 0) : false;
+}
+
+// ---- pass 1: per-point record + per-(frame,sweep,row) histogram --------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kBinThreads) k_bin_count(LidarIn in, uint2* __restrict__ tmp, uint32_t* __restrict__ counts) {
+    const int bs = blockIdx.y, b = bs / in.S;
+    const int beg = in.sweep_off[bs], end = in.sweep_off[bs + 1];
+    const long long chunk0 = (long long)beg + (long long)blockIdx.x * kBinChunk;
+    if (chunk0 >= end) return;
+    __shared__ double sT[12];
+    __shared__ int sRect[kMaxRects * 4];
+    __shared__ uint32_t hist[kH];
+    int nrect; bool flip;
+    load_frame_consts(in, bs, b, MODE, sT, sRect, nrect, flip);
+    for (int r = threadIdx.x; r < kH; r += kBinThreads) hist[r] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < kBinItems; ++it) {
+        const long long i = chunk0 + it * kBinThreads + threadIdx.x;
+        int row = 0; uint32_t cell = 0, bits = 0;
+        const bool ok = (i < end) && point_record<MODE>(in, i, sT, flip, sRect, nrect, row, cell, bits);
+        // warp-aggregated histogram: one shared atomic per distinct row per warp
+        const uint32_t key = ok ? (uint32_t)row : 0xFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (ok && lane == __ffs(peers) - 1) atomicAdd(&hist[row], (uint32_t)__popc(peers));
+        if (i < end) tmp[i] = make_uint2(ok ? (((uint32_t)row << 15) | cell) : kInvalid, bits);
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < kH; r += kBinThreads)
+        if (hist[r]) atomicAdd(&counts[(size_t)bs * kH + r], hist[r]);
+}
+
+// ---- pass 1b: exclusive scan of each sweep's 400 row counts -> absolute starts in `sorted` ------
+__global__ void __launch_bounds__(512) k_bin_scan(const int32_t* __restrict__ sweep_off, const uint32_t* __restrict__ counts,
+                                                  uint32_t* __restrict__ starts) {
+    const int bs = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    __shared__ uint32_t wsum[16];
+    const uint32_t c = t < kH ? counts[(size_t)bs * kH + t] : 0u;
+    uint32_t v = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += n; }
+    if (lane == 31) wsum[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = lane < 16 ? wsum[lane] : 0u;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, s, d); if (lane >= d) s += n; }
+        if (lane < 16) wsum[lane] = s;
+    }
+    __syncthreads();
+    if (t < kH) starts[(size_t)bs * kH + t] = (uint32_t)sweep_off[bs] + (w ? wsum[w - 1] : 0u) + v - c;
+}
+
+// ---- pass 2: scatter records into their row bins ------------------------------------------------
+__global__ void __launch_bounds__(kBinThreads) k_bin_scatter(const int32_t* __restrict__ sweep_off, int S,
+                                                             const uint2* __restrict__ tmp, const uint32_t* __restrict__ starts,
+                                                             uint32_t* __restrict__ cursor, uint2* __restrict__ sorted) {
+    const int bs = blockIdx.y;
+    const int beg = sweep_off[bs], end = sweep_off[bs + 1];
+    const long long chunk0 = (long long)beg + (long long)blockIdx.x * kBinChunk;
+    if (chunk0 >= end) return;
+    __shared__ uint32_t hist[kH];
+    __shared__ uint32_t base[kH];
+    for (int r = threadIdx.x; r < kH; r += kBinThreads) hist[r] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint2 rec[kBinItems];
+    uint32_t lrank[kBinItems];
+#pragma unroll
+    for (int it = 0; it < kBinItems; ++it) {
+        const long long i = chunk0 + it * kBinThreads + threadIdx.x;
+        rec[it] = (i < end) ? tmp[i] : make_uint2(kInvalid, 0u);
+        const bool ok = rec[it].x != kInvalid;
+        const uint32_t key = ok ? (rec[it].x >> 15) : 0xFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        lrank[it] = 0;
+        if (ok) {   // claim-then-broadcast: the group leader reserves popc(peers) slots of the CTA-local bin
+            const int leader = __ffs(peers) - 1;
+            uint32_t b0 = 0;
+            if (lane == leader) b0 = atomicAdd(&hist[key], (uint32_t)__popc(peers));
+            b0 = __shfl_sync(peers, b0, leader);
+            lrank[it] = b0 + (uint32_t)__popc(peers & lt);
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < kH; r += kBinThreads)
+        if (hist[r]) base[r] = starts[(size_t)bs * kH + r] + atomicAdd(&cursor[(size_t)bs * kH + r], hist[r]);
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kBinItems; ++it)
+        if (rec[it].x != kInvalid)
+            sorted[base[rec[it].x >> 15] + lrank[it]] = make_uint2(rec[it].x & 0x7FFFu, rec[it].y);
+}
+
+// ---- pass 3: shared-memory tile raster + TMA bulk store (persistent, double buffered) -----------
+__global__ void __launch_bounds__(kRasterThreads, 1) k_raster_store(const uint2* __restrict__ sorted,
+                                                                    const uint32_t* __restrict__ starts,
+                                                                    const uint32_t* __restrict__ counts,
+                                                                    float* __restrict__ out, int num_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* const buf0 = reinterpret_cast<uint32_t*>(smem_raw);                   // two contiguous tiles
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 2 * kRowTileElems; i += kRasterThreads) buf0[i] = 0u;
+    uint32_t prev_start0 = 0u, prev_cnt0 = 0u, prev_start1 = 0u, prev_cnt1 = 0u;   // last occupant of each buffer
+    __syncthreads();
+
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int cur = it & 1;
+        uint32_t* const tile = buf0 + cur * kRowTileElems;
+        const uint32_t start = starts[t], cnt = counts[t];
+        // the store issued from this buffer two tiles ago must have finished READING shared memory
+        if (tid < kZ) bulk_wait_read<1>();
+        __syncthreads();
+        // restore the all-zero tile: clear exactly the cells the previous occupant touched
+        const uint32_t pstart = cur ? prev_start1 : prev_start0, pcnt = cur ? prev_cnt1 : prev_cnt0;
+        for (uint32_t i = tid; i < pcnt; i += kRasterThreads) tile[sorted[pstart + i].x] = 0u;
+        __syncthreads();
+        // apply this tile's records: warp-aggregated max (dedupe equal cells inside the warp first)
+        for (uint32_t i0 = 0; i0 < cnt; i0 += kRasterThreads) {
+            const uint32_t i = i0 + tid;
+            const bool have = i < cnt;
+            uint2 r = make_uint2(0xFFFFFFFFu, 0u);
+            if (have) r = sorted[start + i];
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, r.x);
+            const uint32_t m = __reduce_max_sync(peers, r.y);
+            if (have && lane == __ffs(peers) - 1) atomicMax(&tile[r.x], m);
+        }
+        fence_proxy_async_smem();     // generic-proxy writes -> visible to the async proxy (TMA)
+        __syncthreads();
+        if (tid < kZ) {
+            // tile t = (frame*S + sweep)*400 + row ; channel = (frame*S + sweep)*29 + zbin
+            const int bs = t / kH, row = t - bs * kH;
+            float* dst = out + ((size_t)(bs * kZ + tid) * kH + row) * kW;
+            bulk_store_s2g(dst, tile + tid * kW, kRowBytes);
+            bulk_commit();
+        }
+        if (cur) { prev_start1 = start; prev_cnt1 = cnt; } else { prev_start0 = start; prev_cnt0 = cnt; }
+    }
+    if (tid < kZ) bulk_wait_all<0>();
+}
+
+// ---- cross-check / fallback: memset + global atomicMax (no binning) -----------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint32_t* __restrict__ out) {
+    const int bs = blockIdx.y, b = bs / in.S;
+    const int beg = in.sweep_off[bs], end = in.sweep_off[bs + 1];
+    const long long chunk0 = (long long)beg + (long long)blockIdx.x * kBinChunk;
+    if (chunk0 >= end) return;
+    __shared__ double sT[12];
+    __shared__ int sRect[kMaxRects * 4];
+    int nrect; bool flip;
+    load_frame_consts(in, bs, b, MODE, sT, sRect, nrect, flip);
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kBinItems; ++it) {
+        const long long i = chunk0 + it * kBinThreads + threadIdx.x;
+        int row; uint32_t cell, bits;
+        if (i < end && point_record<MODE>(in, i, sT, flip, sRect, nrect, row, cell, bits)) {
+            const uint32_t zb = cell / kW, px = cell - zb * kW;
+            atomicMax(out + ((size_t)(bs * kZ + zb) * kH + row) * kW + px, bits);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_transform_points(const T* __restrict__ pts, long long n, long long stride,
+                                                          Pose34 P, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double ox, oy, oz;
+    xform_point(P.m, (double)pts[i * stride], (double)pts[i * stride + 1], (double)pts[i * stride + 2], ox, oy, oz);
+    out[3 * i] = ox; out[3 * i + 1] = oy; out[3 * i + 2] = oz;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// workspace layout: [counts | cursor | starts] (u32 per row bin)  [tmp | sorted] (u64 per point)
+struct WorkspaceLayout {
+    size_t counts, cursor, starts, tmp, sorted, bytes;
+};
+
+WorkspaceLayout layout(long long total_points, int B, int S) {
+    WorkspaceLayout w;
+    const size_t bins = (size_t)B * S * kH;
+    size_t off = 0;
+    w.counts = off; off += align_up(bins * 4, 256);
+    w.cursor = off; off += align_up(bins * 4, 256);
+    w.starts = off; off += align_up(bins * 4, 256);
+    w.tmp = off;    off += align_up((size_t)total_points * 8, 256);
+    w.sorted = off; off += align_up((size_t)total_points * 8, 256);
+    w.bytes = off;
+    return w;
+}
+
+int g_num_sms = 0;
+
+template <int MODE>
+int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int max_sweep_points, float* out,
+                 void* workspace, size_t workspace_bytes, int algo, cudaStream_t st) {
+    if (B <= 0 || S <= 0 || total_points < 0 || max_sweep_points < 0 || !out || !in.sweep_off) return BEVGEN_E_INVALID_ARG;
+    if ((in.rects == nullptr) != (in.nrects == nullptr)) return BEVGEN_E_INVALID_ARG;
+    if ((size_t)B * S * kH > 0x7FFFFFFFull) return BEVGEN_E_UNSUPPORTED;
+    const int chunks = max_sweep_points > 0 ? (max_sweep_points + kBinChunk - 1) / kBinChunk : 0;
+    const dim3 bin_grid(chunks > 0 ? chunks : 1, B * S);
+    if (bin_grid.y > 65535u) return BEVGEN_E_UNSUPPORTED;
+    if (algo == 1) {
+        BEVGEN_CUDA(cudaMemsetAsync(out, 0, (size_t)B * S * kZ * kPlane * sizeof(float), st));
+        if (chunks > 0) {
+            k_scatter_atomic<MODE><<<bin_grid, kBinThreads, 0, st>>>(in, reinterpret_cast<uint32_t*>(out));
+            BEVGEN_CHECK_LAUNCH();
+        }
+        return 0;
+    }
+    if (algo != 0) return BEVGEN_E_INVALID_ARG;
+    if (!workspace || workspace_bytes < bevgen_lidar_workspace_bytes(total_points, B, S)) return BEVGEN_E_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;   // bulk store needs 16 B alignment
+    const WorkspaceLayout L = layout(total_points, B, S);
+    char* wp = static_cast<char*>(workspace);
+    struct { uint32_t *counts, *cursor, *starts; uint2 *tmp, *sorted; } w = {
+        reinterpret_cast<uint32_t*>(wp + L.counts), reinterpret_cast<uint32_t*>(wp + L.cursor),
+        reinterpret_cast<uint32_t*>(wp + L.starts), reinterpret_cast<uint2*>(wp + L.tmp),
+        reinterpret_cast<uint2*>(wp + L.sorted)};
+    const size_t bins = (size_t)B * S * kH;
+    // counts and cursor are adjacent: one clear
+    BEVGEN_CUDA(cudaMemsetAsync(w.counts, 0, L.starts - L.counts, st));
+    if (chunks > 0) {
+        k_bin_count<MODE><<<bin_grid, kBinThreads, 0, st>>>(in, w.tmp, w.counts);
+        BEVGEN_CHECK_LAUNCH();
+    }
+    k_bin_scan<<<B * S, 512, 0, st>>>(in.sweep_off, w.counts, w.starts);
+    BEVGEN_CHECK_LAUNCH();
+    if (chunks > 0) {
+        k_bin_scatter<<<bin_grid, kBinThreads, 0, st>>>(in.sweep_off, S, w.tmp, w.starts, w.cursor, w.sorted);
+        BEVGEN_CHECK_LAUNCH();
+    }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        BEVGEN_CUDA(cudaGetDevice(&dev));
+        BEVGEN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        BEVGEN_CUDA(cudaFuncSetAttribute(k_raster_store, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileBytes));
+    }
+    const int tiles = (int)bins;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;   // persistent: one CTA per SM
+    k_raster_store<<<grid, kRasterThreads, 2 * kTileBytes, st>>>(w.sorted, w.starts, w.counts, out, tiles);
+    BEVGEN_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+}  // namespace bevgen
+
+using namespace bevgen;
+
+extern "C" size_t bevgen_lidar_workspace_bytes(int64_t total_points, int B, int S) {
+    if (total_points < 0 || B <= 0 || S <= 0) return 0;
+    return layout(total_points, B, S).bytes;
+}
+
+extern "C" int bevgen_lidar_bev_fused(const float* pts4, const int32_t* sweep_offsets, const double* rel_tf, int B, int S,
+                                      int64_t total_points, int max_sweep_points, const uint8_t* flip,
+                                      const int32_t* drop_rects, const int32_t* drop_counts, float* out, void* workspace,
+                                      size_t workspace_bytes, int algo, bevgen_stream_t stream) {
+    if (total_points > 0 && (!pts4 || !rel_tf)) return BEVGEN_E_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(pts4) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
+    LidarIn in{reinterpret_cast<const float4*>(pts4), rel_tf, nullptr, nullptr, sweep_offsets, flip, drop_rects, drop_counts, S};
+    return launch_lidar<0>(in, B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bevgen_lidar_bev_ego_f64(const double* pts3, const float* intensity, const int32_t* sweep_offsets, int B, int S,
+                                        int64_t total_points, int max_sweep_points, const uint8_t* flip,
+                                        const int32_t* drop_rects, const int32_t* drop_counts, float* out, void* workspace,
+                                        size_t workspace_bytes, int algo, bevgen_stream_t stream) {
+    if (total_points > 0 && (!pts3 || !intensity)) return BEVGEN_E_INVALID_ARG;
+    LidarIn in{nullptr, nullptr, pts3, intensity, sweep_offsets, flip, drop_rects, drop_counts, S};
+    return launch_lidar<1>(in, B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo,
+                           static_cast<cudaStream_t>(stream));
+}
+
+static int launch_transform(const void* pts, bool f64, int64_t n, int64_t stride, const double* T_host, double* out,
+                            cudaStream_t st) {
+    if (n < 0 || stride < 3 || !T_host) return BEVGEN_E_INVALID_ARG;
+    if (n == 0) return 0;
+    if (!pts || !out) return BEVGEN_E_INVALID_ARG;
+    Pose34 P;
+    for (int i = 0; i < 12; ++i) P.m[i] = T_host[i];
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (f64) k_transform_points<double><<<grid, 256, 0, st>>>(static_cast<const double*>(pts), n, stride, P, out);
+    else     k_transform_points<float><<<grid, 256, 0, st>>>(static_cast<const float*>(pts), n, stride, P, out);
+    BEVGEN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bevgen_transform_points_f32(const float* pts, int64_t n, int64_t stride, const double* T_host, double* out,
+                                           bevgen_stream_t stream) {
+    return launch_transform(pts, false, n, stride, T_host, out, static_cast<cudaStream_t>(stream));
+}
+extern "C" int bevgen_transform_points_f64(const double* pts, int64_t n, int64_t stride, const double* T_host, double* out,
+                                           bevgen_stream_t stream) {
+    return launch_transform(pts, true, n, stride, T_host, out, static_cast<cudaStream_t>(stream));
+}
