@@ -108,13 +108,14 @@ int bevgen_lidar_bev_ego_f64(const double *pts3, const float *intensity, const i
  * frame_map int32 [B,4] = lane_begin, lane_count, cw_begin, cw_count (rows into lanes / cws)
  * ego_T     float64 [B,9] = 3x3 world->ego matrix of utils.py:35-45 per frame
  * max_prims = max over frames of lane_count + cw_count
+ * max_polyline_verts = longest polyline in the table (<= BEVGEN_MAX_POLYLINE_VERTS; sizes the per-warp scratch)
  * out float32 [B,9,400,720], fully written.  flip / drop_* as above.
  * ------------------------------------------------------------------------------------- */
 size_t bevgen_map_workspace_bytes(int B);
 
 int bevgen_map_raster(const double *verts, const int32_t *pl_off, const int32_t *lanes,
                       const int32_t *cws, const int32_t *frame_map, const double *ego_T,
-                      int B, int max_prims,
+                      int B, int max_prims, int max_polyline_verts,
                       const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,
                       float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
 

@@ -1,0 +1,252 @@
+"""Train-time BEV augmentation (reference utils.py:394-517) on the GPU.
+
+Host responsibilities (Python, as in the reference):
+  * draw the random parameters from Python's global ``random`` in the reference's exact call
+    order (utils.py:398, 421-422, 455-456, 488-494) so a seeded run makes the same decisions;
+  * the handful of GT-box / label updates (utils.py:401-414, 441-448, 478-479);
+  * cv2.getRotationMatrix2D + warpAffine's matrix inversion in float64 (libm cos/sin).
+Device: one fused gather kernel per batch (csrc/augment.cu) for flip -> rotate -> scale -> dropout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+import random
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+from .bev_ops import _dev, _ptr, _require_cuda, _stream_ptr
+from .constants import GRID_HEIGHT_PX, GRID_WIDTH_PX, INTENTIONS_MAP
+
+_CV_PI = 3.1415926535897932384626433832795
+
+
+@dataclasses.dataclass
+class AugParams:
+    """One frame's augmentation decisions (what the reference draws inside its four random_* calls)."""
+    flip: bool = False
+    angle_deg: Optional[float] = None          # None = no rotation
+    scale: Optional[float] = None              # None = no scaling
+    rects: List[Tuple[int, int, int, int]] = dataclasses.field(default_factory=list)   # (y0, x0, ph, pw)
+
+    @property
+    def needs_gather(self) -> bool:
+        """True when a resampling pass is needed; flip / dropout alone can be fused into generation."""
+        return self.angle_deg is not None or self.scale is not None
+
+
+def draw_aug_params(rng=random, angle_range_deg=(-15.0, 15.0), scale_range=(0.95, 1.05), dropout_prob=0.1,
+                    patch_size_range=(20, 50), num_patches_range=(1, 5)) -> AugParams:
+    """Consumes ``rng`` exactly like augment_bev does (utils.py:508-511 -> :398, :421-422, :455-456, :488-494)."""
+    p = AugParams()
+    p.flip = rng.random() < 0.5
+    if rng.random() < 0.5:
+        p.angle_deg = rng.uniform(angle_range_deg[0], angle_range_deg[1])
+    if rng.random() < 0.5:
+        p.scale = rng.uniform(scale_range[0], scale_range[1])
+    if rng.random() < dropout_prob:
+        for _ in range(rng.randint(num_patches_range[0], num_patches_range[1])):
+            ph = rng.randint(patch_size_range[0], patch_size_range[1])
+            pw = rng.randint(patch_size_range[0], patch_size_range[1])
+            y0 = rng.randint(0, max(0, GRID_HEIGHT_PX - ph))
+            x0 = rng.randint(0, max(0, GRID_WIDTH_PX - pw))
+            p.rects.append((y0, x0, ph, pw))
+    return p
+
+
+# ------------------------------------------------------------------------------- matrices (host, float64)
+def rotation_matrix_2d(angle_deg: float) -> np.ndarray:
+    """cv2.getRotationMatrix2D((360.0, 200.0), angle_deg, 1.0) (utils.py:425-428) restated in float64."""
+    cx, cy = GRID_WIDTH_PX / 2.0, GRID_HEIGHT_PX / 2.0
+    a = angle_deg * (_CV_PI / 180.0)
+    alpha, beta = math.cos(a) * 1.0, math.sin(a) * 1.0
+    return np.array([[alpha, beta, (1 - alpha) * cx - beta * cy],
+                     [-beta, alpha, beta * cx + (1 - alpha) * cy]], dtype=np.float64)
+
+
+def invert_affine_2x3(M: np.ndarray) -> np.ndarray:
+    """The inversion cv2.warpAffine performs on the forward matrix (no WARP_INVERSE_MAP), same op order."""
+    m = [float(v) for v in np.asarray(M, np.float64).reshape(6)]
+    D = m[0] * m[4] - m[1] * m[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = m[4] * D, m[0] * D
+    m[0] = A11; m[1] *= -D; m[3] *= -D; m[4] = A22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return np.array(m, np.float64).reshape(2, 3)
+
+
+def pack_params(params: Sequence[AugParams]) -> np.ndarray:
+    """-> uint8 array holding ``len(params)`` C structs ``bevgen_aug_params`` (include/bevgen.h)."""
+    arr = (_native.AugParams * len(params))()
+    for i, p in enumerate(params):
+        a = arr[i]
+        if p.angle_deg is not None:
+            mi = invert_affine_2x3(rotation_matrix_2d(p.angle_deg)).reshape(6)
+            for k in range(6):
+                a.minv[k] = mi[k]
+            a.do_rotate = 1
+        if p.scale is not None:
+            a.scale = float(p.scale)
+            a.do_scale = 1
+        a.do_flip = 1 if p.flip else 0
+        if len(p.rects) > 5:
+            raise ValueError("at most 5 dropout rectangles (utils.py:485)")
+        a.n_rects = len(p.rects)
+        for j, (y0, x0, ph, pw) in enumerate(p.rects):
+            a.rects[4 * j:4 * j + 4] = [int(y0), int(x0), int(ph), int(pw)]
+    return np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+
+
+def fusion_arrays(params: Sequence[AugParams]):
+    """(flip uint8 [B], rects int32 [B,5,4], counts int32 [B]) for the generator-fused flip/dropout of frames
+    that need no resampling; frames that do get flip=0 / no rects here (the gather kernel applies them)."""
+    B = len(params)
+    flip = np.zeros(B, np.uint8)
+    rects = np.zeros((B, 5, 4), np.int32)
+    cnt = np.zeros(B, np.int32)
+    for b, p in enumerate(params):
+        if p.needs_gather:
+            continue
+        flip[b] = 1 if p.flip else 0
+        cnt[b] = len(p.rects)
+        for j, r in enumerate(p.rects):
+            rects[b, j] = r
+    return flip, rects, cnt
+
+
+# ------------------------------------------------------------------------------- device entry
+def augment_grid(src: torch.Tensor, params: Sequence[AugParams], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Apply per-frame ``params`` to ``src`` [B,C,400,720] (float32 CUDA); returns a new tensor (dst != src)."""
+    _require_cuda()
+    if src.dim() != 4 or src.shape[2:] != (GRID_HEIGHT_PX, GRID_WIDTH_PX) or src.dtype != torch.float32:
+        raise ValueError("src must be float32 [B,C,400,720]")
+    src = src.contiguous()
+    B, Cc = int(src.shape[0]), int(src.shape[1])
+    if len(params) != B:
+        raise ValueError("one AugParams per frame")
+    if out is None:
+        out = torch.empty_like(src)
+    elif out.shape != src.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.data_ptr() == src.data_ptr():
+        raise ValueError("out must be a distinct contiguous float32 tensor of the same shape")
+    dparams = _dev(pack_params(params), torch.uint8, src.device)
+    rc = _native.lib().bevgen_augment(_ptr(src), _ptr(out), B, Cc, _ptr(dparams), _stream_ptr())
+    _native.check(rc, "bevgen_augment")
+    return out
+
+
+# ------------------------------------------------------------------------------- GT (host, reference semantics)
+def _wrap(a: np.ndarray) -> np.ndarray:
+    return np.arctan2(np.sin(a), np.cos(a))
+
+
+_FLIP_SWAP = {INTENTIONS_MAP["TURN_LEFT"]: INTENTIONS_MAP["TURN_RIGHT"],
+              INTENTIONS_MAP["TURN_RIGHT"]: INTENTIONS_MAP["TURN_LEFT"],
+              INTENTIONS_MAP["LEFT_CHANGE_LANE"]: INTENTIONS_MAP["RIGHT_CHANGE_LANE"],
+              INTENTIONS_MAP["RIGHT_CHANGE_LANE"]: INTENTIONS_MAP["LEFT_CHANGE_LANE"]}
+
+
+def apply_gt(p: AugParams, boxes: np.ndarray, intentions: np.ndarray):
+    """GT side of utils.py:401-414 (flip), :441-448 (rotate about the ego origin) and :478-479 (scale),
+    in place on ``boxes`` (K,5: cx,cy,w,l,yaw) and ``intentions`` (K,), in the reference's order."""
+    if p.flip:
+        if boxes.shape[0] > 0:
+            boxes[:, 1] *= -1
+            boxes[:, 4] *= -1
+            boxes[:, 4] = _wrap(boxes[:, 4])
+        if intentions.shape[0] > 0:
+            orig = intentions.copy()
+            for old, new in _FLIP_SWAP.items():
+                intentions[orig == old] = new
+    if p.angle_deg is not None and boxes.shape[0] > 0:
+        ang = np.radians(p.angle_deg)
+        cx, cy = boxes[:, 0].copy(), boxes[:, 1].copy()
+        ca, sa = np.cos(ang), np.sin(ang)
+        boxes[:, 0], boxes[:, 1] = cx * ca - cy * sa, cx * sa + cy * ca
+        boxes[:, 4] += ang
+        boxes[:, 4] = _wrap(boxes[:, 4])
+    if p.scale is not None and boxes.shape[0] > 0:
+        boxes[:, :4] *= p.scale
+    return boxes, intentions
+
+
+# ------------------------------------------------------------------------------- reference signatures (numpy)
+def _apply_np(lidar_bev: np.ndarray, map_bev: np.ndarray, p: AugParams):
+    dev = _require_cuda()
+    lo = augment_grid(_dev(lidar_bev, torch.float32, dev)[None], [p])[0].cpu().numpy()
+    mo = augment_grid(_dev(map_bev, torch.float32, dev)[None], [p])[0].cpu().numpy()
+    return lo, mo
+
+
+def random_flip_bev(lidar_bev, map_bev, gt_boxes_xywha, gt_intentions):
+    """Drop-in for utils.py:394-415."""
+    p = AugParams(flip=random.random() < 0.5)
+    if p.flip:
+        lidar_bev, map_bev = _apply_np(lidar_bev, map_bev, p)
+        apply_gt(p, gt_boxes_xywha, gt_intentions)
+    return lidar_bev, map_bev, gt_boxes_xywha, gt_intentions
+
+
+def random_rotate_bev(lidar_bev, map_bev, gt_boxes_xywha, angle_range_deg=(-15.0, 15.0)):
+    """Drop-in for utils.py:417-449."""
+    if random.random() < 0.5:
+        p = AugParams(angle_deg=random.uniform(angle_range_deg[0], angle_range_deg[1]))
+        lidar_bev, map_bev = _apply_np(lidar_bev, map_bev, p)
+        apply_gt(p, gt_boxes_xywha, np.zeros((0,), np.int64))
+    return lidar_bev, map_bev, gt_boxes_xywha
+
+
+def random_scale_bev(lidar_bev, map_bev, gt_boxes_xywha, scale_range=(0.95, 1.05)):
+    """Drop-in for utils.py:451-480."""
+    if random.random() < 0.5:
+        p = AugParams(scale=random.uniform(scale_range[0], scale_range[1]))
+        lidar_bev, map_bev = _apply_np(lidar_bev, map_bev, p)
+        apply_gt(p, gt_boxes_xywha, np.zeros((0,), np.int64))
+    return lidar_bev, map_bev, gt_boxes_xywha
+
+
+def random_bev_dropout(lidar_bev, map_bev, dropout_prob=0.1, patch_size_range=(20, 50), num_patches_range=(1, 5)):
+    """Drop-in for utils.py:482-498 (mutates and returns its inputs, like the reference)."""
+    if random.random() < dropout_prob:
+        p = AugParams()
+        for _ in range(random.randint(num_patches_range[0], num_patches_range[1])):
+            ph = random.randint(patch_size_range[0], patch_size_range[1])
+            pw = random.randint(patch_size_range[0], patch_size_range[1])
+            y0 = random.randint(0, max(0, GRID_HEIGHT_PX - ph))
+            x0 = random.randint(0, max(0, GRID_WIDTH_PX - pw))
+            p.rects.append((y0, x0, ph, pw))
+        if isinstance(lidar_bev, torch.Tensor):
+            lidar_bev.copy_(augment_grid(lidar_bev[None], [p])[0])
+            map_bev.copy_(augment_grid(map_bev[None], [p])[0])
+        else:
+            lo, mo = _apply_np(lidar_bev, map_bev, p)
+            lidar_bev[...] = lo          # in place, as utils.py:496-497
+            map_bev[...] = mo
+    return lidar_bev, map_bev
+
+
+def augment_bev(lidar_bev, map_bev, gt_dict):
+    """Drop-in for utils.py:500-517: numpy (or CUDA tensor) grids in, same kind out, GT dict of tensors.
+
+    Inputs are never modified (the reference copies at utils.py:503-506).  With CUDA tensors in, the
+    result stays on the device (no 344 MB host round trip)."""
+    gb, gi = gt_dict["boxes_xywha"], gt_dict["intentions"]
+    boxes = gb.clone().numpy() if isinstance(gb, torch.Tensor) else gb.copy()
+    intents = gi.clone().numpy() if isinstance(gi, torch.Tensor) else gi.copy()
+    p = draw_aug_params(random)
+    apply_gt(p, boxes, intents)
+    on_device = isinstance(lidar_bev, torch.Tensor)
+    dev = _require_cuda()
+    ld = lidar_bev if on_device else _dev(lidar_bev, torch.float32, dev)
+    md = map_bev if isinstance(map_bev, torch.Tensor) else _dev(map_bev, torch.float32, dev)
+    lo = augment_grid(ld[None], [p])[0]
+    mo = augment_grid(md[None], [p])[0]
+    if not on_device:
+        lo, mo = lo.cpu().numpy(), mo.cpu().numpy()
+    gt = {"boxes_xywha": torch.from_numpy(np.asarray(boxes)).float(), "intentions": torch.from_numpy(np.asarray(intents)).long()}
+    return lo, mo, gt

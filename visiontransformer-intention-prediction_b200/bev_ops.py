@@ -25,7 +25,7 @@ import torch
 from . import _native
 from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LIDAR_SWEEPS)
 
-ALGO_TILED, ALGO_ATOMIC = 0, 1
+ALGO_TILED, ALGO_ATOMIC, ALGO_FUSED, ALGO_FUSED_DEDUPE = 0, 1, 2, 3
 MAX_DROP_RECTS = 5
 
 
@@ -118,7 +118,7 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
     L = _native.lib()
     ws = None
     wbytes = 0
-    if algo == ALGO_TILED:
+    if algo != ALGO_ATOMIC:
         wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
         ws = workspace.get("lidar", wbytes, device)
     rc = L.bevgen_lidar_bev_fused(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
@@ -152,13 +152,22 @@ def lidar_bev_from_ego_points(points3, intensity, sweep_offsets, num_frames: int
         raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
     L = _native.lib()
     ws, wbytes = None, 0
-    if algo == ALGO_TILED:
+    if algo != ALGO_ATOMIC:
         wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
         ws = workspace.get("lidar", wbytes, device)
     rc = L.bevgen_lidar_bev_ego_f64(_ptr(pts), _ptr(inten), _ptr(off), B, S, n, int(max_sweep_points),
                                     _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
     _native.check(rc, "bevgen_lidar_bev_ego_f64")
     return out
+
+
+def fused_spin_timeout_flag(num_frames: int, num_sweeps: int = LIDAR_SWEEPS) -> int:
+    """Debug/test hook: 1 if the fused kernel's bounded dependency spin ever timed out in the last
+    ALGO_FUSED call on this device (results would then be incomplete); synchronises the stream."""
+    device = _require_cuda()
+    ws = workspace.get("lidar", 0, device)
+    torch.cuda.current_stream().synchronize()
+    return int(ws[: (num_frames * num_sweeps + 1) * 4].view(torch.int32)[num_frames * num_sweeps].item())
 
 
 # =========================================================================== reference signatures

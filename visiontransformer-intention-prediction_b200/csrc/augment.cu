@@ -1,3 +1,161 @@
-// placeholder until the augmentation kernels land (next commit)
+// augment.cu -- train-time BEV augmentation: flip -> rotate -> scale -> dropout in ONE gather pass (sm_100a).
+//
+// Replaces the image part of reference utils.py:394-498 (augment_bev, utils.py:500-517, applies them in this
+// order).  The reference materialises up to four full copies of the 299-channel grids (np.flip, 299 x
+// cv2.warpAffine + np.stack, 299 x cv2.resize + np.stack); here every output pixel is produced once:
+//
+//   out(y,x) = 0                                   if (y,x) is inside a dropout rectangle       utils.py:496
+//            = S(y,x),  S = resize+crop/pad of R   (cv2.resize INTER_LINEAR, utils.py:457-471)  if do_scale
+//            = R(y,x),  R = warpAffine of F        (cv2.warpAffine INTER_LINEAR, utils.py:430-433) if do_rotate
+//            = F(y,x) = src(y, 719-x) or src(y,x)  (np.flip axis 2, utils.py:399)
+//
+// Exactness: R is a deterministic float32 function of F (fixed-point coordinates on a 1/32-pixel grid,
+// float32 weights, 4-tap sum evaluated left to right without FMA), so recomputing the <= 4 R values a
+// scaled pixel needs reproduces the reference's intermediate rounding bit for bit -- no intermediate
+// image, 1 read + 1 write of the grids instead of 3 + 3.
+// Geometry (tap offsets, weights) depends only on (y,x), not on the channel: it is computed once per
+// thread and reused for all C channels of the frame.
 #include "bevgen_common.cuh"
-extern "C" int bevgen_augment(const float*, float*, int, int, const bevgen_aug_params*, bevgen_stream_t) { return BEVGEN_E_UNSUPPORTED; }
+
+namespace bevgen {
+namespace {
+
+constexpr int kAugThreads = 240;                 // 3 blocks per 720-pixel row
+
+struct RotTap {                                  // 4 taps of cv2's remapBilinear for one destination pixel
+    int off[4];                                  // offset into the source plane, -1 = outside (BORDER_CONSTANT 0)
+    float w[4];
+};
+
+__device__ __forceinline__ int flip_x(int x, bool flip) { return flip ? kW - 1 - x : x; }
+
+// cv2.warpAffine coordinate scheme (imgwarp.cpp WarpAffineInvoker, INTER_LINEAR): AB_BITS 10, INTER_BITS 5
+__device__ __forceinline__ RotTap rot_taps(const double* __restrict__ M, int y, int x, bool flip) {
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[4], (double)y), M[5]), 1024.0)) + 16;
+    const int ad = __double2int_rn(__dmul_rn(__dmul_rn(M[0], (double)x), 1024.0));
+    const int bd = __double2int_rn(__dmul_rn(__dmul_rn(M[3], (double)x), 1024.0));
+    const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+    int sx = X >> 5, sy = Y >> 5;
+    sx = max(-32768, min(32767, sx)); sy = max(-32768, min(32767, sy));      // saturate_cast<short>
+    const float fx = __fmul_rn((float)(X & 31), 0.03125f), fy = __fmul_rn((float)(Y & 31), 0.03125f);
+    const float tx0 = __fsub_rn(1.f, fx), ty0 = __fsub_rn(1.f, fy);
+    RotTap t;
+    t.w[0] = __fmul_rn(ty0, tx0); t.w[1] = __fmul_rn(ty0, fx); t.w[2] = __fmul_rn(fy, tx0); t.w[3] = __fmul_rn(fy, fx);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int xx = sx + (k & 1), yy = sy + (k >> 1);
+        t.off[k] = (xx >= 0 && xx < kW && yy >= 0 && yy < kH) ? yy * kW + flip_x(xx, flip) : -1;
+    }
+    return t;
+}
+
+__device__ __forceinline__ float rot_eval(const float* __restrict__ plane, const RotTap& t) {
+    const float v0 = t.off[0] >= 0 ? __ldg(plane + t.off[0]) : 0.f;
+    const float v1 = t.off[1] >= 0 ? __ldg(plane + t.off[1]) : 0.f;
+    const float v2 = t.off[2] >= 0 ? __ldg(plane + t.off[2]) : 0.f;
+    const float v3 = t.off[3] >= 0 ? __ldg(plane + t.off[3]) : 0.f;
+    float r = __fmul_rn(v0, t.w[0]);
+    r = __fadd_rn(r, __fmul_rn(v1, t.w[1]));
+    r = __fadd_rn(r, __fmul_rn(v2, t.w[2]));
+    r = __fadd_rn(r, __fmul_rn(v3, t.w[3]));
+    return r;
+}
+
+// cv2.resize INTER_LINEAR source taps for destination index d (resize.cpp): f = (float)((d+0.5)*scale-0.5)
+__device__ __forceinline__ void resize_tap(int d, int dsize, int ssize, int& s0, int& s1, float& w0, float& w1) {
+    const double inv_scale = __ddiv_rn((double)dsize, (double)ssize);
+    const double scale = __ddiv_rn(1.0, inv_scale);
+    float f = __double2float_rn(__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5));
+    int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+    s0 = s;
+    s1 = s + 1 < ssize ? s + 1 : ssize - 1;
+    w0 = __fsub_rn(1.f, f);
+    w1 = f;
+}
+
+__global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict__ src, float* __restrict__ dst, int C,
+                                                         const bevgen_aug_params* __restrict__ params) {
+    const int x = blockIdx.x * kAugThreads + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    __shared__ bevgen_aug_params P;
+    {
+        const int* g = reinterpret_cast<const int*>(params + b);
+        int* s = reinterpret_cast<int*>(&P);
+        for (int i = threadIdx.x; i < (int)(sizeof(bevgen_aug_params) / 4); i += kAugThreads) s[i] = g[i];
+    }
+    __syncthreads();
+    const bool flip = P.do_flip != 0, rot = P.do_rotate != 0;
+    int nrect = P.n_rects;
+    nrect = nrect > kMaxRects ? kMaxRects : (nrect < 0 ? 0 : nrect);
+    const bool dropped = nrect && in_rects(P.rects, nrect, y, x);
+
+    // ---- geometry: which R (or F) values does this output pixel need, with which weights -------------
+    int nq = 1;                                    // 1 source point, or 4 for a scaled pixel
+    int qy[4] = {y, y, y, y}, qx[4] = {x, x, x, x};
+    float wx0 = 1.f, wx1 = 0.f, wy0 = 1.f, wy1 = 0.f;
+    bool outside = false;                          // scaled-down frame: zero padding around the resized image
+    if (P.do_scale) {
+        const int nh = (int)__dmul_rn((double)kH, P.scale), nw = (int)__dmul_rn((double)kW, P.scale);   // utils.py:457
+        const bool crop = P.scale > 1.0;                                                             // utils.py:464
+        const int h0 = crop ? (nh - kH) / 2 : (kH - nh) / 2, w0 = crop ? (nw - kW) / 2 : (kW - nw) / 2;
+        const int ry = crop ? y + h0 : y - h0, rx = crop ? x + w0 : x - w0;
+        if (ry < 0 || ry >= nh || rx < 0 || rx >= nw) {
+            outside = true;
+        } else {
+            int sx0, sx1, sy0, sy1;
+            resize_tap(rx, nw, kW, sx0, sx1, wx0, wx1);
+            resize_tap(ry, nh, kH, sy0, sy1, wy0, wy1);
+            nq = 4;
+            qy[0] = sy0; qx[0] = sx0; qy[1] = sy0; qx[1] = sx1; qy[2] = sy1; qx[2] = sx0; qy[3] = sy1; qx[3] = sx1;
+        }
+    }
+    RotTap tap[4];
+    int direct[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        direct[q] = qy[q] * kW + flip_x(qx[q], flip);
+        if (rot && q < nq) tap[q] = rot_taps(P.minv, qy[q], qx[q], flip);
+    }
+
+    // ---- channel loop ---------------------------------------------------------------------------------
+    const size_t pix = (size_t)y * kW + x;
+    const float* sp = src + (size_t)b * C * kPlane;
+    float* dp = dst + (size_t)b * C * kPlane + pix;
+    if (dropped || outside) {
+        for (int c = 0; c < C; ++c) dp[(size_t)c * kPlane] = 0.f;
+        return;
+    }
+#pragma unroll 2
+    for (int c = 0; c < C; ++c) {
+        const float* plane = sp + (size_t)c * kPlane;
+        float r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q < nq) r[q] = rot ? rot_eval(plane, tap[q]) : __ldg(plane + direct[q]);
+        float v = r[0];
+        if (nq == 4) {     // horizontal pass then vertical pass, float32, no FMA (resize.cpp HResize/VResize)
+            const float top = __fadd_rn(__fmul_rn(r[0], wx0), __fmul_rn(r[1], wx1));
+            const float bot = __fadd_rn(__fmul_rn(r[2], wx0), __fmul_rn(r[3], wx1));
+            v = __fadd_rn(__fmul_rn(top, wy0), __fmul_rn(bot, wy1));
+        }
+        dp[(size_t)c * kPlane] = v;
+    }
+}
+
+}  // namespace
+}  // namespace bevgen
+
+using namespace bevgen;
+
+extern "C" int bevgen_augment(const float* src, float* dst, int B, int C, const bevgen_aug_params* params,
+                              bevgen_stream_t stream) {
+    if (B <= 0 || C <= 0 || !src || !dst || !params || src == dst) return BEVGEN_E_INVALID_ARG;
+    if (B > 65535) return BEVGEN_E_UNSUPPORTED;
+    const dim3 grid(kW / kAugThreads, kH, B);
+    k_augment<<<grid, kAugThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, C, params);
+    BEVGEN_CHECK_LAUNCH();
+    return 0;
+}

@@ -53,8 +53,8 @@ __device__ __forceinline__ void xform_point(const double* __restrict__ T, double
     oz = __fma_rn(T[11], 1.0, __fma_rn(T[10], z, __fma_rn(T[9], y, __fma_rn(T[8], x, 0.0))));
 }
 
-// utils.py:80-95.  Returns false when the point is masked out (utils.py:83-87).
-__device__ __forceinline__ bool lidar_voxel(double x, double y, double z, int& py, int& px, int& zb) {
+// utils.py:80-95 evaluated literally (three IEEE float64 divisions).  Returns false when masked out.
+static __device__ __noinline__ bool lidar_voxel_exact(double x, double y, double z, int& py, int& px, int& zb) {
     const double fx = floor(__dadd_rn(kOffX, __ddiv_rn(y, kVoxel)));   // utils.py:80
     const double fy = floor(__dsub_rn(kOffY, __ddiv_rn(x, kVoxel)));   // utils.py:81
     // NaN / +-inf / out-of-range fail these compares, as the reference's INT_MIN cast does
@@ -62,6 +62,30 @@ __device__ __forceinline__ bool lidar_voxel(double x, double y, double z, int& p
     const double fz = floor(__dmul_rn(__ddiv_rn(__dsub_rn(z, kZMin), kZSpan), (double)kZ));   // utils.py:94
     int b = (int)fz;
     b = b < 0 ? 0 : (b > kZ - 1 ? kZ - 1 : b);                                                // utils.py:95
+    px = (int)fx; py = (int)fy; zb = b;
+    return true;
+}
+
+// Same result, bit for bit, without the divisions on the common path.
+//   reference:  r = fl(360 + fl(y / 0.2d)),  0.2d = 0.2(1 + 5.6e-17)
+//   fast:       t = fl(fma(y, 5, 360))
+// For -1 <= value <= 721:  |r - t| < (|5y| + |360 + 5y|) * 2^-51 < 1e-12, so floor(r) == floor(t) whenever
+// t is further than kEps = 1e-6 from an integer; the (rare) near-integer points take the literal path.
+// Same argument for 300 - x/0.2 and for (z + 2)/5.8d*29 vs (z + 2)*5  (29/5.8d = 5(1 + 3e-17)).
+__device__ __forceinline__ bool lidar_voxel(double x, double y, double z, int& py, int& px, int& zb) {
+    if (!(z >= kZMin && z < kZMax)) return false;                       // utils.py:86-87 (exact compares)
+    const double tx = __fma_rn(y, 5.0, kOffX);
+    const double ty = __fma_rn(x, -5.0, kOffY);
+    if (!(tx > -0.5 && tx < (double)kW + 0.5 && ty > -0.5 && ty < (double)kH + 0.5)) return false;   // NaN -> false
+    const double tz = __dmul_rn(__dsub_rn(z, kZMin), 5.0);
+    const double fx = floor(tx), fy = floor(ty), fz = floor(tz);
+    constexpr double kEps = 1e-6;
+    const double dx = __dsub_rn(tx, fx), dy = __dsub_rn(ty, fy), dz = __dsub_rn(tz, fz);
+    if (dx < kEps || dx > 1.0 - kEps || dy < kEps || dy > 1.0 - kEps || dz < kEps || dz > 1.0 - kEps)
+        return lidar_voxel_exact(x, y, z, py, px, zb);
+    if (!(fx >= 0.0 && fx < (double)kW && fy >= 0.0 && fy < (double)kH)) return false;
+    int b = (int)fz;
+    b = b > kZ - 1 ? kZ - 1 : b;
     px = (int)fx; py = (int)fy; zb = b;
     return true;
 }

@@ -15,6 +15,9 @@
 // of the tile, so no memset pass and no read-modify-write of the 334 MB/frame output ever happens.
 #include "bevgen_common.cuh"
 
+#include <cstdlib>
+#include <vector>
+
 namespace bevgen {
 
 namespace {
@@ -39,30 +42,63 @@ struct LidarIn {
     int S;
 };
 
+// Raw point as loaded from HBM.  Loads are issued for ALL of a thread's items before the first use, so
+// kBinItems independent 16 B (MODE 0) / 28 B (MODE 1) requests are in flight per thread.
+template <int MODE> struct RawPoint;
+template <> struct RawPoint<0> { float4 p; };
+template <> struct RawPoint<1> { double x, y, z; float v; };
+
+template <int MODE>
+__device__ __forceinline__ RawPoint<MODE> load_point(const LidarIn& in, long long i, bool in_range);
+template <>
+__device__ __forceinline__ RawPoint<0> load_point<0>(const LidarIn& in, long long i, bool in_range) {
+    RawPoint<0> r;
+    r.p = in_range ? __ldcs(in.pts4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);   // streaming 16 B load, fully coalesced
+    return r;
+}
+template <>
+__device__ __forceinline__ RawPoint<1> load_point<1>(const LidarIn& in, long long i, bool in_range) {
+    RawPoint<1> r;
+    r.x = r.y = r.z = 0.0; r.v = 0.f;
+    if (in_range) {
+        r.x = __ldcs(in.pts3 + 3 * i); r.y = __ldcs(in.pts3 + 3 * i + 1); r.z = __ldcs(in.pts3 + 3 * i + 2);
+        r.v = __ldcs(in.intensity + i);
+    }
+    return r;
+}
+
 // One point -> (row, cell-in-row-tile, intensity bits) or invalid.  MODE 0 transforms first.
 template <int MODE>
-__device__ __forceinline__ bool point_record(const LidarIn& in, long long i, const double* sT, bool flip,
-                                             const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits) {
-    double x, y, z;
-    float v;
-    if (MODE == 0) {
-        const float4 p = __ldcs(in.pts4 + i);             // streaming 16 B load, fully coalesced
-        xform_point(sT, (double)p.x, (double)p.y, (double)p.z, x, y, z);
-        v = p.w;
-    } else {
-        x = __ldcs(in.pts3 + 3 * i); y = __ldcs(in.pts3 + 3 * i + 1); z = __ldcs(in.pts3 + 3 * i + 2);
-        v = __ldcs(in.intensity + i);
-    }
-    int py, px, zb;
-    if (!lidar_voxel(x, y, z, py, px, zb)) return false;
+__device__ __forceinline__ bool point_record(const RawPoint<MODE>& raw, const double* sT, bool flip,
+                                             const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits);
+template <>
+__device__ __forceinline__ bool point_record<0>(const RawPoint<0>& raw, const double* sT, bool flip,
+                                                const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits) {
     // max with the +0.0 initial grid: only strictly positive intensities can change a voxel
     // (documented domain: finite or +inf, >= 0; then float max == unsigned max on the bit pattern)
-    if (!(v > 0.0f)) return false;
+    if (!(raw.p.w > 0.0f)) return false;
+    double x, y, z;
+    xform_point(sT, (double)raw.p.x, (double)raw.p.y, (double)raw.p.z, x, y, z);
+    int py, px, zb;
+    if (!lidar_voxel(x, y, z, py, px, zb)) return false;
     if (flip) px = kW - 1 - px;                           // utils.py:399 fused
     if (nrect && in_rects(sRect, nrect, py, px)) return false;   // utils.py:496 fused
     row = py;
     cell = (uint32_t)(zb * kW + px);
-    bits = __float_as_uint(v);
+    bits = __float_as_uint(raw.p.w);
+    return true;
+}
+template <>
+__device__ __forceinline__ bool point_record<1>(const RawPoint<1>& raw, const double*, bool flip,
+                                                const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits) {
+    if (!(raw.v > 0.0f)) return false;
+    int py, px, zb;
+    if (!lidar_voxel(raw.x, raw.y, raw.z, py, px, zb)) return false;
+    if (flip) px = kW - 1 - px;
+    if (nrect && in_rects(sRect, nrect, py, px)) return false;
+    row = py;
+    cell = (uint32_t)(zb * kW + px);
+    bits = __float_as_uint(raw.v);
     return true;
 }
 
@@ -90,11 +126,17 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_count(LidarIn in, uint2* __
     for (int r = threadIdx.x; r < kH; r += kBinThreads) hist[r] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    RawPoint<MODE> raw[kBinItems];
+#pragma unroll
+    for (int it = 0; it < kBinItems; ++it) {
+        const long long i = chunk0 + it * kBinThreads + threadIdx.x;
+        raw[it] = load_point<MODE>(in, i, i < end);
+    }
 #pragma unroll
     for (int it = 0; it < kBinItems; ++it) {
         const long long i = chunk0 + it * kBinThreads + threadIdx.x;
         int row = 0; uint32_t cell = 0, bits = 0;
-        const bool ok = (i < end) && point_record<MODE>(in, i, sT, flip, sRect, nrect, row, cell, bits);
+        const bool ok = (i < end) && point_record<MODE>(raw[it], sT, flip, sRect, nrect, row, cell, bits);
         // warp-aggregated histogram: one shared atomic per distinct row per warp
         const uint32_t key = ok ? (uint32_t)row : 0xFFFFu;
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
@@ -217,10 +259,139 @@ __global__ void __launch_bounds__(kRasterThreads, 1) k_raster_store(const uint2*
     if (tid < kZ) bulk_wait_all<0>();
 }
 
+// ---- fused persistent kernel: TMA zero fill + L2-resident atomic scatter --------------------------
+// One cooperative launch for the whole batch; warp-specialised CTAs:
+//   producer warps (kProducers, lane 0 only): walk the fill chunks g = 0 .. B*S*1160-1; each chunk is ONE TMA
+//       bulk store of an immutable all-zero shared-memory tile (kFillBytes) to out + g*kFillBytes -- no LSU
+//       traffic, no registers.  When the store has completed (bulk wait_group), the producer publishes it:
+//       proxy fence + __threadfence + atomicAdd(done[sweep of g]).  Producers never wait on anything else,
+//       so the fill stream runs at TMA/HBM speed from the first to the last byte of the batch.
+//   consumer warps: walk the scatter chunks (1024 points each, sweep-major).  A sweep region (29 channels =
+//       33.4 MB = 1160 fill chunks) may only be scattered into after ALL its fill chunks have landed:
+//       ld.acquire spin on done[js] == 1160 (bounded).  Then transform, bin and RED.MAX into out.
+// Scatter trails the fill front by about one sweep region, so its atomics hit lines that are still dirty in
+// the 126 MB L2 and cost no DRAM read-modify-write.  All CTAs are co-resident (cooperative launch) and
+// producers are independent of consumers, hence no deadlock.
+constexpr int kFillRows = 10;
+constexpr int kFillBytes = kFillRows * kRowBytes;                    // 28 800 B
+constexpr int kFillPerSweep = kZ * kH / kFillRows;                   // 1160 chunks per (frame, sweep)
+constexpr int kProducers = 4;                                        // producer warps per CTA
+constexpr int kConsumerThreads = 128;
+constexpr int kFusedThreads = kProducers * 32 + kConsumerThreads;    // 256
+constexpr int kScatItems = kBinChunk / kConsumerThreads;             // 8 points per consumer thread per chunk
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kConsumerThreads) : "memory"); }
+
+template <int MODE, bool DEDUPE>
+__global__ void __launch_bounds__(kFusedThreads) k_fill_scatter(LidarIn in, uint32_t* __restrict__ out,
+                                                                uint32_t* __restrict__ done, uint32_t* __restrict__ err_flag,
+                                                                int num_sweeps_total, int chunks_per_sweep) {
+    extern __shared__ __align__(128) unsigned char zero_tile[];
+    __shared__ double sT[12];
+    __shared__ int sRect[kMaxRects * 4];
+    __shared__ int s_ok;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kFillBytes / 16; i += kFusedThreads) reinterpret_cast<uint4*>(zero_tile)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) s_ok = 1;          // sticky: only ever cleared (on a spin timeout)
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    if (warp < kProducers) {
+        // ===================== producer: TMA zero fill =====================
+        if (lane != 0) return;
+        const long long total_fill = (long long)num_sweeps_total * kFillPerSweep;
+        const long long stride = (long long)gridDim.x * kProducers;
+        long long prev = -1;
+        for (long long g = (long long)blockIdx.x * kProducers + warp; g < total_fill; g += stride) {
+            bulk_store_s2g(reinterpret_cast<unsigned char*>(out) + g * kFillBytes, zero_tile, kFillBytes);
+            bulk_commit();
+            if (prev >= 0) {                 // one store stays in flight while the previous one is published
+                bulk_wait_all<1>();
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                atomicAdd(&done[prev / kFillPerSweep], 1u);
+            }
+            prev = g;
+        }
+        if (prev >= 0) {
+            bulk_wait_all<0>();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+            atomicAdd(&done[prev / kFillPerSweep], 1u);
+        }
+        return;
+    }
+
+    // ===================== consumers: transform + bin + RED.MAX =====================
+    const int ctid = tid - kProducers * 32;
+    const long long total_scat = (long long)num_sweeps_total * chunks_per_sweep;
+    int cur_bs = -1;                 // sweep whose constants are in shared memory
+    int ready_bs = -1;               // highest sweep known to be completely filled (monotone in hs order)
+    for (long long hs = blockIdx.x; hs < total_scat; hs += gridDim.x) {
+        const int bs = (int)(hs / chunks_per_sweep);
+        const int c = (int)(hs - (long long)bs * chunks_per_sweep);
+        const int beg = in.sweep_off[bs], end = in.sweep_off[bs + 1];
+        const long long chunk0 = (long long)beg + (long long)c * kBinChunk;
+        if (chunk0 >= end) continue;                         // uniform: ragged sweep, nothing in this chunk
+        if (bs != ready_bs) {
+            if (ctid == 0) {
+                unsigned spins = 0;
+                while (ld_acquire_u32(&done[bs]) < (uint32_t)kFillPerSweep) {
+                    __nanosleep(100);
+                    if (++spins > 20000000u) { s_ok = 0; atomicExch(err_flag, 1u); break; }   // never hang the GPU
+                }
+            }
+            consumer_sync();                                 // also orders the previous chunk's sT readers
+            ready_bs = bs;
+        }
+        if (bs != cur_bs) {
+            if (MODE == 0 && ctid < 12) sT[ctid] = in.rel_tf[(size_t)bs * 16 + ctid];
+            const int b0 = bs / in.S;
+            int nr = in.nrects ? in.nrects[b0] : 0;
+            nr = nr > kMaxRects ? kMaxRects : nr;
+            if (ctid < 4 * nr) sRect[ctid] = in.rects[(size_t)b0 * kMaxRects * 4 + ctid];
+            cur_bs = bs;
+            consumer_sync();
+        }
+        const int b = bs / in.S;
+        int nrect = in.nrects ? in.nrects[b] : 0;
+        nrect = nrect > kMaxRects ? kMaxRects : nrect;
+        const bool flip = in.flip ? (in.flip[b] != 0) : false;
+        if (!s_ok) continue;
+        uint32_t* region = out + (size_t)bs * kZ * kPlane;
+        RawPoint<MODE> raw[kScatItems];
+#pragma unroll
+        for (int it = 0; it < kScatItems; ++it) {
+            const long long i = chunk0 + it * kConsumerThreads + ctid;
+            raw[it] = load_point<MODE>(in, i, i < end);
+        }
+#pragma unroll
+        for (int it = 0; it < kScatItems; ++it) {
+            const long long i = chunk0 + it * kConsumerThreads + ctid;
+            int row = 0; uint32_t cell = 0, bits = 0;
+            const bool ok = (i < end) && point_record<MODE>(raw[it], sT, flip, sRect, nrect, row, cell, bits);
+            const uint32_t zb = cell / kW, px = cell - zb * kW;
+            const uint32_t vox = (zb * kH + (uint32_t)row) * kW + px;
+            if (DEDUPE) {      // warp-aggregated: one RED per distinct voxel per warp
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ok ? vox : 0xFFFFFFFFu);
+                const uint32_t m = __reduce_max_sync(peers, bits);
+                if (ok && lane == __ffs(peers) - 1) atomicMax(region + vox, m);
+            } else if (ok) {
+                atomicMax(region + vox, bits);
+            }
+        }
+    }
+}
+
 // ---- cross-check / fallback: memset + global atomicMax (no binning) -----------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint32_t* __restrict__ out) {
-    const int bs = blockIdx.y, b = bs / in.S;
+__global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint32_t* __restrict__ out, int bs0) {
+    const int bs = bs0 + blockIdx.y, b = bs / in.S;
     const int beg = in.sweep_off[bs], end = in.sweep_off[bs + 1];
     const long long chunk0 = (long long)beg + (long long)blockIdx.x * kBinChunk;
     if (chunk0 >= end) return;
@@ -229,11 +400,17 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint
     int nrect; bool flip;
     load_frame_consts(in, bs, b, MODE, sT, sRect, nrect, flip);
     __syncthreads();
+    RawPoint<MODE> raw[kBinItems];
+#pragma unroll
+    for (int it = 0; it < kBinItems; ++it) {
+        const long long i = chunk0 + it * kBinThreads + threadIdx.x;
+        raw[it] = load_point<MODE>(in, i, i < end);
+    }
 #pragma unroll
     for (int it = 0; it < kBinItems; ++it) {
         const long long i = chunk0 + it * kBinThreads + threadIdx.x;
         int row; uint32_t cell, bits;
-        if (i < end && point_record<MODE>(in, i, sT, flip, sRect, nrect, row, cell, bits)) {
+        if (i < end && point_record<MODE>(raw[it], sT, flip, sRect, nrect, row, cell, bits)) {
             const uint32_t zb = cell / kW, px = cell - zb * kW;
             atomicMax(out + ((size_t)(bs * kZ + zb) * kH + row) * kW + px, bits);
         }
@@ -284,9 +461,115 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
     if (algo == 1) {
         BEVGEN_CUDA(cudaMemsetAsync(out, 0, (size_t)B * S * kZ * kPlane * sizeof(float), st));
         if (chunks > 0) {
-            k_scatter_atomic<MODE><<<bin_grid, kBinThreads, 0, st>>>(in, reinterpret_cast<uint32_t*>(out));
+            k_scatter_atomic<MODE><<<bin_grid, kBinThreads, 0, st>>>(in, reinterpret_cast<uint32_t*>(out), 0);
             BEVGEN_CHECK_LAUNCH();
         }
+        return 0;
+    }
+    if (algo == 5 || algo == 6) {
+        // sweep-group interleave: zero k sweep regions (k*33.4 MB), then scatter those k sweeps while their lines are
+        // still L2-resident.  algo 5 = one stream; algo 6 = scatter on an aux stream (overlaps the next group's fill)
+        static int group = 0;
+        if (group == 0) { const char* e = getenv("BEVGEN_SWEEP_GROUP"); group = e ? atoi(e) : 2; if (group < 1) group = 1; }
+        static cudaStream_t aux2 = nullptr;
+        static std::vector<cudaEvent_t> evs2;
+        static cudaEvent_t evb = nullptr, eve = nullptr;
+        const int total = B * S;
+        const int ngroups = (total + group - 1) / group;
+        cudaStream_t sc = st;
+        if (algo == 6) {
+            if (!aux2) {
+                BEVGEN_CUDA(cudaStreamCreateWithFlags(&aux2, cudaStreamNonBlocking));
+                BEVGEN_CUDA(cudaEventCreateWithFlags(&evb, cudaEventDisableTiming));
+                BEVGEN_CUDA(cudaEventCreateWithFlags(&eve, cudaEventDisableTiming));
+            }
+            while ((int)evs2.size() < ngroups) {
+                cudaEvent_t e;
+                BEVGEN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                evs2.push_back(e);
+            }
+            BEVGEN_CUDA(cudaEventRecord(evb, st));
+            BEVGEN_CUDA(cudaStreamWaitEvent(aux2, evb, 0));
+            sc = aux2;
+        }
+        const size_t sweep_elems = (size_t)kZ * kPlane;
+        for (int g = 0; g < ngroups; ++g) {
+            const int s0 = g * group, ns = (s0 + group <= total) ? group : total - s0;
+            BEVGEN_CUDA(cudaMemsetAsync(out + (size_t)s0 * sweep_elems, 0, (size_t)ns * sweep_elems * sizeof(float), st));
+            if (chunks > 0) {
+                if (algo == 6) {
+                    BEVGEN_CUDA(cudaEventRecord(evs2[g], st));
+                    BEVGEN_CUDA(cudaStreamWaitEvent(aux2, evs2[g], 0));
+                }
+                k_scatter_atomic<MODE><<<dim3(chunks, ns), kBinThreads, 0, sc>>>(in, reinterpret_cast<uint32_t*>(out), s0);
+                BEVGEN_CHECK_LAUNCH();
+            }
+        }
+        if (algo == 6) {
+            BEVGEN_CUDA(cudaEventRecord(eve, aux2));
+            BEVGEN_CUDA(cudaStreamWaitEvent(st, eve, 0));
+        }
+        return 0;
+    }
+    if (algo == 4) {
+        // frame-pipelined: zero fill of frame f+1 (caller's stream) overlaps the atomic scatter of frame f (aux stream)
+        static cudaStream_t aux = nullptr;
+        static std::vector<cudaEvent_t> evs;
+        static cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+        if (!aux) {
+            BEVGEN_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+            BEVGEN_CUDA(cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming));
+            BEVGEN_CUDA(cudaEventCreateWithFlags(&ev_end, cudaEventDisableTiming));
+        }
+        while ((int)evs.size() < B) {
+            cudaEvent_t e;
+            BEVGEN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            evs.push_back(e);
+        }
+        BEVGEN_CUDA(cudaEventRecord(ev_begin, st));
+        BEVGEN_CUDA(cudaStreamWaitEvent(aux, ev_begin, 0));
+        const size_t frame_elems = (size_t)S * kZ * kPlane;
+        const dim3 fgrid(chunks > 0 ? chunks : 1, S);
+        for (int f = 0; f < B; ++f) {
+            BEVGEN_CUDA(cudaMemsetAsync(out + (size_t)f * frame_elems, 0, frame_elems * sizeof(float), st));
+            if (chunks > 0) {
+                BEVGEN_CUDA(cudaEventRecord(evs[f], st));
+                BEVGEN_CUDA(cudaStreamWaitEvent(aux, evs[f], 0));
+                k_scatter_atomic<MODE><<<fgrid, kBinThreads, 0, aux>>>(in, reinterpret_cast<uint32_t*>(out), f * S);
+                BEVGEN_CHECK_LAUNCH();
+            }
+        }
+        BEVGEN_CUDA(cudaEventRecord(ev_end, aux));
+        BEVGEN_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
+        return 0;
+    }
+    if (algo == 2 || algo == 3) {   // fused fill + scatter (3 = with warp-level dedupe)
+        const size_t need = ((size_t)B * S + 64) * sizeof(uint32_t);
+        if (!workspace || workspace_bytes < need) return BEVGEN_E_WORKSPACE;
+        if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
+        uint32_t* done = static_cast<uint32_t*>(workspace);
+        uint32_t* err_flag = done + (size_t)B * S;
+        BEVGEN_CUDA(cudaMemsetAsync(done, 0, need, st));
+        void (*kern)(LidarIn, uint32_t*, uint32_t*, uint32_t*, int, int) =
+            algo == 3 ? k_fill_scatter<MODE, true> : k_fill_scatter<MODE, false>;
+        static int grid_cached[4] = {0, 0, 0, 0};
+        int& grid = grid_cached[(algo - 2) * 2 + MODE];
+        if (grid == 0) {
+            int dev = 0, sms = 0, occ = 0;
+            BEVGEN_CUDA(cudaGetDevice(&dev));
+            BEVGEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            BEVGEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFusedThreads, kFillBytes));
+            if (occ < 1) return BEVGEN_E_UNSUPPORTED;
+            if (occ > 4) occ = 4;
+            grid = sms * occ;
+        }
+        uint32_t* outu = reinterpret_cast<uint32_t*>(out);
+        int nsw = B * S, cps = chunks > 0 ? chunks : 1;
+        LidarIn in_copy = in;
+        void* args[] = {&in_copy, &outu, &done, &err_flag, &nsw, &cps};
+        BEVGEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(kFusedThreads), args,
+                                                (size_t)kFillBytes, st));
+        ++g_launch_count;
         return 0;
     }
     if (algo != 0) return BEVGEN_E_INVALID_ARG;
