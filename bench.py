@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- BEV input generation throughput on B200 (BASELINE.json metric: BEV frames/s, Gpoints/s,
+fraction of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5]
+
+One "step" = one pass of the hot path over one batch of synthetic frames per GPU.  Default workload =
+BASELINE.json configs[1]: multi-sweep aggregation, 10 sweeps x 100 000 points, batch 32 per GPU
+(the other configs are selectable and are parity-test cases).  For N > 1 launch under torchrun (one
+process per GPU); frames shard independently, no collective on the data path (weak scaling); NCCL only
+gathers the timing (max over ranks).
+
+Printed JSON (rank 0, one line): the driver contract plus
+  roofline      dominant kernel: achieved algorithmic GB/s (live CUDA-event time of that kernel inside the
+                timed region) vs the measured HBM peak in MEASURED_PEAKS.json
+  kernels       per-kernel ms/step and launches/step measured the same way
+  e2e           same metric through the public host-facing API: pinned host buffers -> H2D -> kernels ->
+                device-resident model inputs + D2H read of a per-frame probe, all inside the timed region
+  cpu_baseline  the reference's numpy/OpenCV path (oracle/numpy_port.py) timed on this box's host cores
+`--impl reference` times that CPU path alone (all host cores, one frame per worker process per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+LIDAR_FRAME_BYTES = 290 * 400 * 720 * 4      # 334 080 000
+MAP_FRAME_BYTES = 9 * 400 * 720 * 4          # 10 368 000
+FALLBACK_HBM_GBS = 6650.0                    # /opt/skills/guides/B200_PROFILING.md fallback
+
+WORKLOADS = {
+    "c2": dict(desc="configs[1]: multi-sweep aggregation, 10 sweeps x 100k pts, synthetic ego poses", batch=32, map=False, aug=False),
+    "c3": dict(desc="configs[2]: LiDAR + HD-map rasterized channels (425 lanes, 20 crosswalks)", batch=32, map=True, aug=False),
+    "c4": dict(desc="configs[3]: dense/skewed scene, 1M pts/frame in 4 clusters", batch=32, map=False, aug=False),
+    "c5": dict(desc="configs[4]: LiDAR + map + flip/rotate/scale/dropout augmentation", batch=16, map=True, aug=True),
+}
+
+
+# ----------------------------------------------------------------------------------- workload
+def make_frames(workload: str, batch: int, points: int, rank: int):
+    import bevgen_b200 as bg
+    syn = bg.synthetic
+    md = syn.synthetic_map() if WORKLOADS[workload]["map"] else None
+    frames = []
+    for i in range(batch):
+        idx = rank * batch + i
+        if workload == "c2":
+            frames.append(syn.frame_c2(idx, n=points))
+        elif workload == "c4":
+            frames.append(syn.frame_c4(idx, n=points))
+        else:
+            frames.append(syn.frame_c3(idx, n=points, map_data=md))
+    return frames, md
+
+
+def frame_bytes(frame_points: int, with_map: bool, map_verts: int) -> int:
+    """algorithmic bytes per frame."""
+    b = frame_points * 16 + 10 * 128 + LIDAR_FRAME_BYTES
+    if with_map:
+        b += MAP_FRAME_BYTES + map_verts * 16
+    return b
+
+
+# ----------------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    """One frame through the numpy/OpenCV port, exactly the stages Dataset.__getitem__ runs."""
+    workload, points, idx, map_path, seed = args
+    import random as _r
+    import bevgen_b200 as bg
+    from oracle import numpy_port as npp
+    syn = bg.synthetic
+    f = syn.frame_c4(idx, n=points) if workload == "c4" else (syn.frame_c2(idx, n=points) if workload == "c2" else syn.frame_c3(idx, n=points, map_data={}))
+    t0 = time.perf_counter()
+    lid = npp.frame_lidar(f.points4, f.sweep_offsets, f.sweep_poses, f.current_pose)
+    if map_path:
+        keys = ["tx_m", "ty_m", "tz_m", "qx", "qy", "qz", "qw"]
+        mp = npp.map_raster(map_path, dict(zip(keys, f.current_pose.tolist())))
+        if workload == "c5":
+            _r.seed(seed)
+            p = bg.augment.draw_aug_params(_r)
+            npp.augment(lid, mp, p.flip, p.angle_deg, p.scale, p.rects)
+    return time.perf_counter() - t0
+
+
+def cpu_reference(workload: str, points: int, steps: int, warmup: int, workers: int, budget_s: float = 150.0):
+    """frames/s of the CPU path with `workers` processes, each step = one frame per worker."""
+    import multiprocessing as mp
+    import tempfile
+    import bevgen_b200 as bg
+    map_path = None
+    if WORKLOADS[workload]["map"]:
+        map_path = os.path.join(tempfile.gettempdir(), f"bevgen_bench_map_{os.getpid()}.json")
+        bg.synthetic.write_map_json(bg.synthetic.synthetic_map(), map_path)
+    ctx = mp.get_context("fork")
+    step_times = []
+    t_begin = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        for s in range(warmup + steps):
+            jobs = [(workload, points, s * workers + w, map_path, 1000 * 5 + s * workers + w) for w in range(workers)]
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                step_times.append(dt)
+            if time.perf_counter() - t_begin > budget_s and len(step_times) >= 1:
+                break
+    if map_path:
+        os.unlink(map_path)
+    total = sum(step_times)
+    return workers * len(step_times) / total, total / len(step_times), len(step_times)
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = min(host_threads(), 32)
+    wl = WORKLOADS[args.workload]
+    fps, step_s, nsteps = cpu_reference(args.workload, args.points, args.steps, args.warmup, workers)
+    pts_frame = 10 * args.points
+    line = {
+        "impl": "reference", "metric": "bev_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": nsteps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "gpoints_per_s": fps * pts_frame / 1e9,
+        "config": {"workload": wl["desc"], "batch": workers, "sweeps": 10, "points_per_sweep": args.points,
+                   "note": "reference CPU path (numpy/OpenCV port of utils.py), one frame per worker process per step"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
+                         "sample": f"{nsteps} steps x {workers} frames ({workers} worker processes, library-default threads each)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int) -> None:
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.splitlines():
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------- ours
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import bevgen_b200 as bg
+    from bevgen_b200 import _native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _native.lib()
+
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
+    algo = {"atomic": bg.ALGO_ATOMIC, "tiled": bg.ALGO_TILED, "fused": bg.ALGO_FUSED, "memset": bg.ALGO_MEMSET_ATOMIC}[args.algo]
+    frames, md = make_frames(args.workload, B, args.points, rank)
+    table = bg.MapTable([bg.maps.parse_map_dict(md)]) if wl["map"] else None
+    batch = bg.FrameBatch.pack(frames, 10, map_ids=[0] * B if wl["map"] else None)
+    gen = bg.BevGenerator(table, algo=algo, device=dev)
+    aug = None
+    if wl["aug"]:
+        import random
+        aug = []
+        for i in range(B):
+            random.seed(1000 * 5 + rank * B + i)
+            aug.append(bg.draw_aug_params(random))
+    S = 10
+    out_l = torch.empty((B, S * 29, 400, 720), dtype=torch.float32, device=dev)
+    out_m = torch.empty((B, 9, 400, 720), dtype=torch.float32, device=dev) if wl["map"] else None
+    dvc = gen.upload(batch)                       # device-resident inputs for the kernel-only metric
+    torch.cuda.synchronize()
+
+    # ---- parity gate before any timing: frame 0 of this rank vs the C oracle, bit for bit ----------------
+    parity = "skipped"
+    if not args.no_parity:
+        from oracle import c_oracle as co
+        r = gen.generate(batch, aug, dev=dvc, with_map=wl["map"], out_lidar=out_l, out_map=out_m)
+        f0 = frames[0]
+        want = co.lidar_bev_fused(f0.points4, f0.sweep_offsets, f0.rel_tf, S)
+        wantm = None
+        if wl["map"]:
+            T3 = bg.pose.map_matrix_from_pose(f0.current_pose[0], f0.current_pose[1], f0.current_pose[3:7])
+            wantm = co.map_raster_flat(co.flatten_map(md), T3)
+        if aug is not None:
+            p = aug[0]
+            for name in ("l", "m"):
+                g = want if name == "l" else wantm
+                if p.flip: g = co.flip_w(g)
+                if p.angle_deg is not None: g = co.rotate(g, p.angle_deg)
+                if p.scale is not None: g = co.scale(g, p.scale)
+                g = np.ascontiguousarray(g).copy()
+                if p.rects: co.dropout(g, p.rects)
+                if name == "l": want = g
+                else: wantm = g
+        ok = bool(torch.equal(r["lidar_bev"][0].cpu(), torch.from_numpy(want)))
+        if wl["map"]:
+            ok = ok and bool(torch.equal(r["map_bev"][0].cpu(), torch.from_numpy(wantm)))
+        if not ok:
+            raise RuntimeError("parity check against the C oracle FAILED; refusing to time a wrong kernel")
+        parity = "bit-exact vs oracle (frame 0)"
+
+    def step_resident():
+        gen.generate(batch, aug, dev=dvc, with_map=wl["map"], out_lidar=out_l, out_map=out_m)
+
+    probe_host = torch.empty((B, 720), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        r = gen.generate(batch, aug, with_map=wl["map"], out_lidar=out_l, out_map=out_m)   # H2D from pinned inside
+        probe_host.copy_(r["lidar_bev"][:, 14, 200, :], non_blocking=True)              # D2H read of the result
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- kernel-only metric (inputs resident in HBM), per-kernel event timing on --------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                           # nvidia-smi sampling spans warm-up + all timed regions below
+        time.sleep(0.3)
+    launches0 = _native.launch_count()
+    _native.timing_enable(True)
+    _native.timing_collect()
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    _native.timing_collect()                      # drop warm-up records
+    launches0 = _native.launch_count()
+    total_ms = timed(step_resident, args.steps, 0)
+    launches = _native.launch_count() - launches0
+    ktimes = _native.timing_collect()
+    _native.timing_enable(False)
+    # ---- same loop without the timing events: the headline device-resident number ------------------------
+    total_ms_plain = timed(step_resident, args.steps, 1)
+    # ---- end to end through the host-facing API -----------------------------------------------------------
+    e2e_ms = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    K = args.steps
+    frames_total = world * B * K
+    value = frames_total / (total_ms_plain / 1e3)
+    pts_frame = int(batch.num_points / B)
+    verts = int(table.verts.shape[0]) if table is not None else 0
+    fbytes = frame_bytes(pts_frame, wl["map"], verts)
+
+    kernels = {n: {"ms_per_step": ms / K, "launches_per_step": c / K} for n, (c, ms) in ktimes.items()}
+    own_bytes = {   # algorithmic bytes one launch of each kernel must move, per frame
+        "k_zero_fill_tma": LIDAR_FRAME_BYTES, "cudaMemsetAsync": LIDAR_FRAME_BYTES, "k_raster_store": LIDAR_FRAME_BYTES,
+        "k_fill_scatter": LIDAR_FRAME_BYTES + pts_frame * 16, "k_scatter_atomic": pts_frame * 16,
+        "k_bin_count": pts_frame * 24, "k_bin_scatter": pts_frame * 12, "k_map_expand": MAP_FRAME_BYTES,
+        "k_augment": 2 * (LIDAR_FRAME_BYTES + (MAP_FRAME_BYTES if wl["map"] else 0)),
+    }
+    peak = FALLBACK_HBM_GBS
+    peak_src = "fallback"
+    mp_path = ROOT / "MEASURED_PEAKS.json"
+    if mp_path.exists():
+        try:
+            peak = float(json.loads(mp_path.read_text())["hbm_gbs"]); peak_src = "measured"
+        except Exception:
+            pass
+    roofline = None
+    mine = {n: k for n, k in kernels.items() if n != "cudaMemsetAsync"} or kernels
+    if mine:
+        dom = max(mine, key=lambda n: mine[n]["ms_per_step"])
+        k = kernels[dom]
+        per_launch_ms = k["ms_per_step"] / max(k["launches_per_step"], 1e-9)
+        frames_per_launch = B / max(k["launches_per_step"], 1e-9) if dom != "k_augment" else B
+        bytes_launch = own_bytes.get(dom, fbytes) * frames_per_launch
+        achieved = bytes_launch / (per_launch_ms / 1e3) / 1e9
+        traffic = None
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists():
+            try:
+                traffic = json.loads(tpath.read_text()).get(dom)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_launch, "ms_per_launch": per_launch_ms}
+    step_gbs = fbytes * B / (total_ms_plain / K / 1e3) / 1e9
+
+    e2e_value = frames_total / (e2e_ms / 1e3)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        workers = min(host_threads(), 32)
+        cfps, cstep, cn = cpu_reference(args.workload, args.points, 2, 1, workers, budget_s=60.0)
+        cpu = {"value": cfps, "unit": "frames/s", "cores": workers, "kind": "port",
+               "sample": f"{cn} steps x {workers} frames of the same workload through oracle/numpy_port.py "
+                         f"({workers} worker processes, one frame each per step; {cstep:.2f} s/step)"}
+
+    line = {
+        "metric": "bev_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": total_ms_plain / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "batch_per_gpu": B, "sweeps": S, "points_per_frame": pts_frame, "algo": args.algo,
+                   "l2": f"per step inputs {batch.h2d_bytes/1e6:.0f} MB + outputs {B*LIDAR_FRAME_BYTES/1e9:.1f} GB >> 126 MB L2",
+                   "parity": parity, "sharding": "frames independent per rank, no data-path collective"},
+        "gpoints_per_s": value * pts_frame / 1e9,
+        "bytes_per_frame": fbytes, "step_algorithmic_gbs": step_gbs, "step_frac_of_peak": step_gbs / peak,
+        "roofline": roofline, "kernels": kernels, "ms_per_step_with_event_timing": total_ms / K,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": batch.h2d_bytes,
+                "d2h_bytes_per_step": int(probe_host.numel() * 4), "ms_per_step": e2e_ms / K,
+                "note": "pinned host frames -> H2D -> kernels -> device-resident [B,290,400,720] model input; D2H = per-frame probe row"},
+        "gpu_launches": int(launches), "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", default="atomic", choices=["atomic", "tiled", "fused", "memset"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--points", type=int, default=100_000, help="points per sweep")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,10 @@ void bevgen_constants(double *out);
 const char *bevgen_error_string(int code);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t bevgen_launch_count(void);
+/* optional per-kernel timing: when enabled every launch is bracketed by CUDA events on its stream;
+ * collect() synchronises them and writes "name count total_ms" lines into buf (host), then resets. */
+void bevgen_timing_enable(int on);
+int bevgen_timing_collect(char *buf, size_t cap);
 
 /* ---------------------------------------------------------------------------------------
  * transform_points -- utils.py:27-33.  out[i,:] = (T . [x y z 1]^T)[:3] in float64, FMA chain
@@ -81,8 +85,11 @@ int bevgen_transform_points_f64(const double *pts, int64_t n, int64_t stride, co
  *               -- only meaningful when no rotate/scale follows for that frame
  *
  * max_sweep_points: max over sweeps of the row count (host knows it; sizes the grid).
- * algo: 0 = tiled (bin by row, shared-memory tile, TMA bulk store)   [default]
- *       1 = atomic (memset + global atomicMax)                        [cross-check / fallback]
+ * algo: 0 = tiled   bin by (sweep,row) -> shared-memory tile + warp-aggregated atomicMax -> TMA bulk store
+ *       1 = atomic  TMA zero-fill kernel + global atomicMax scatter kernel
+ *       2 = fused   one persistent cooperative kernel: TMA zero fill + dependent atomic scatter (3 = + warp dedupe)
+ *       4 = cudaMemsetAsync + the scatter kernel of algo 1 (library fill; comparison point)
+ *       All produce identical bits; workspace is needed for 0, 2, 3.
  * ------------------------------------------------------------------------------------- */
 size_t bevgen_lidar_workspace_bytes(int64_t total_points, int B, int S);
 

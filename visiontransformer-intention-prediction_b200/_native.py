@@ -61,6 +61,8 @@ PROTOTYPES = {
     "bevgen_constants": (None, [_p]),
     "bevgen_error_string": (C.c_char_p, [_i]),
     "bevgen_launch_count": (_i64, []),
+    "bevgen_timing_enable": (None, [_i]),
+    "bevgen_timing_collect": (_i, [C.c_char_p, _sz]),
     "bevgen_transform_points_f32": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "bevgen_transform_points_f64": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "bevgen_lidar_workspace_bytes": (_sz, [_i64, _i, _i]),
@@ -106,3 +108,18 @@ def check(code: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().bevgen_launch_count())
+
+
+def timing_enable(on: bool) -> None:
+    lib().bevgen_timing_enable(1 if on else 0)
+
+
+def timing_collect() -> dict:
+    """{kernel name: (launches, total_ms)} since the last collect (synchronises the recorded events)."""
+    buf = C.create_string_buffer(1 << 14)
+    lib().bevgen_timing_collect(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name] = (int(cnt), float(ms))
+    return out

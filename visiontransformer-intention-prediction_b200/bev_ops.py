@@ -25,7 +25,12 @@ import torch
 from . import _native
 from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LIDAR_SWEEPS)
 
-ALGO_TILED, ALGO_ATOMIC, ALGO_FUSED, ALGO_FUSED_DEDUPE = 0, 1, 2, 3
+# LiDAR algorithms (all bit-identical; bench.py / DESIGN.md record the measured ranking):
+#   TILED          bin by (sweep,row) -> shared-memory tile, warp-aggregated atomicMax -> TMA bulk store of the tile
+#   ATOMIC         TMA zero-fill kernel + one global-atomicMax scatter kernel            (hand-written only)
+#   FUSED[_DEDUPE] one persistent cooperative kernel: TMA zero fill + dependent atomic scatter
+#   MEMSET_ATOMIC  cudaMemsetAsync + the same scatter kernel (library fill, kept as a comparison point)
+ALGO_TILED, ALGO_ATOMIC, ALGO_FUSED, ALGO_FUSED_DEDUPE, ALGO_MEMSET_ATOMIC = 0, 1, 2, 3, 4
 MAX_DROP_RECTS = 5
 
 
@@ -118,7 +123,7 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
     L = _native.lib()
     ws = None
     wbytes = 0
-    if algo != ALGO_ATOMIC:
+    if algo not in (ALGO_ATOMIC, ALGO_MEMSET_ATOMIC):
         wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
         ws = workspace.get("lidar", wbytes, device)
     rc = L.bevgen_lidar_bev_fused(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
@@ -152,7 +157,7 @@ def lidar_bev_from_ego_points(points3, intensity, sweep_offsets, num_frames: int
         raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
     L = _native.lib()
     ws, wbytes = None, 0
-    if algo != ALGO_ATOMIC:
+    if algo not in (ALGO_ATOMIC, ALGO_MEMSET_ATOMIC):
         wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
         ws = workspace.get("lidar", wbytes, device)
     rc = L.bevgen_lidar_bev_ego_f64(_ptr(pts), _ptr(inten), _ptr(off), B, S, n, int(max_sweep_points),

@@ -155,7 +155,7 @@ extern "C" int bevgen_augment(const float* src, float* dst, int B, int C, const 
     if (B <= 0 || C <= 0 || !src || !dst || !params || src == dst) return BEVGEN_E_INVALID_ARG;
     if (B > 65535) return BEVGEN_E_UNSUPPORTED;
     const dim3 grid(kW / kAugThreads, kH, B);
-    k_augment<<<grid, kAugThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, C, params);
-    BEVGEN_CHECK_LAUNCH();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BEVGEN_LAUNCH("k_augment", st, k_augment<<<grid, kAugThreads, 0, st>>>(src, dst, C, params));
     return 0;
 }

@@ -32,6 +32,18 @@ extern long long g_launch_count;           // host-side counter (cabi.cu)
         if (e__ != cudaSuccess) return (int)e__;               \
     } while (0)
 
+// optional per-kernel timing (bench.py): CUDA events recorded on the launching stream around each launch
+void timing_begin(const char* name, cudaStream_t st);
+void timing_end(cudaStream_t st);
+
+#define BEVGEN_LAUNCH(name, st, ...)                           \
+    do {                                                       \
+        ::bevgen::timing_begin(name, st);                      \
+        __VA_ARGS__;                                           \
+        ::bevgen::timing_end(st);                              \
+        BEVGEN_CHECK_LAUNCH();                                 \
+    } while (0)
+
 #define BEVGEN_CUDA(call)                                      \
     do {                                                       \
         cudaError_t e__ = (call);                              \

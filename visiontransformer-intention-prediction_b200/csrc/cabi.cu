@@ -1,8 +1,71 @@
 // cabi.cu -- library-level entry points of the C ABI (include/bevgen.h).
 #include "bevgen_common.cuh"
 
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
 namespace bevgen {
 long long g_launch_count = 0;
+
+namespace {
+struct TimedLaunch { const char* name; cudaEvent_t e0, e1; };
+bool g_timing = false;
+std::vector<TimedLaunch> g_pending;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t g_open = nullptr;
+const char* g_open_name = nullptr;
+
+cudaEvent_t get_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+void timing_begin(const char* name, cudaStream_t st) {
+    if (!g_timing) return;
+    g_open = get_event();
+    g_open_name = name;
+    cudaEventRecord(g_open, st);
+}
+void timing_end(cudaStream_t st) {
+    if (!g_timing || !g_open) return;
+    cudaEvent_t e1 = get_event();
+    cudaEventRecord(e1, st);
+    g_pending.push_back({g_open_name, g_open, e1});
+    g_open = nullptr;
+}
+}  // namespace bevgen
+
+extern "C" void bevgen_timing_enable(int on) { bevgen::g_timing = on != 0; }
+
+// Synchronises the recorded events, writes "name count total_ms\n" lines into buf, clears the record.
+extern "C" int bevgen_timing_collect(char* buf, size_t cap) {
+    using namespace bevgen;
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto& t : g_pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(t.e1);
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) { auto& a = agg[t.name]; a.first += 1; a.second += ms; }
+        g_event_pool.push_back(t.e0);
+        g_event_pool.push_back(t.e1);
+    }
+    g_pending.clear();
+    std::string out;
+    char line[160];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof line, "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (!buf || cap == 0) return (int)out.size();
+    const size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+    return (int)n;
 }
 
 extern "C" int bevgen_abi_version(void) { return BEVGEN_ABI_VERSION; }

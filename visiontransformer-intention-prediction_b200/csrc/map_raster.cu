@@ -271,12 +271,11 @@ extern "C" int bevgen_map_raster(const double* verts, const int32_t* pl_off, con
             attr_smem = smem;
         }
         const dim3 grid((max_prims + kDrawWarps - 1) / kDrawWarps, B);
-        k_map_draw<<<grid, kDrawThreads, smem, st>>>(in, planes, maxv);
-        BEVGEN_CHECK_LAUNCH();
+        BEVGEN_LAUNCH("k_map_draw", st, k_map_draw<<<grid, kDrawThreads, smem, st>>>(in, planes, maxv));
     }
     const long long total4 = (long long)B * kMapC * kH * (kW / 4);
-    k_map_expand<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(planes, out, flip, drop_rects, drop_counts, total4);
-    BEVGEN_CHECK_LAUNCH();
+    BEVGEN_LAUNCH("k_map_expand", st,
+                  k_map_expand<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(planes, out, flip, drop_rects, drop_counts, total4));
     return 0;
 }
 

@@ -1,0 +1,131 @@
+"""Batched frame -> BEV tensors pipeline: what ``Dataset.__getitem__`` x B + ``collate_fn`` do in the
+reference (dataset.py:262-361, :137-150), as a handful of kernel launches per batch.
+
+    host frames (raw sweep points, poses, map id)
+        -> FrameBatch.pack()      pose prep with the reference's numpy/scipy calls (dataset.py:285-301,
+                                  :323-339; utils.py:121-129), everything packed into PINNED host buffers
+        -> BevGenerator.generate  H2D copies, LiDAR kernels, map rasterizer, [fused augmentation]
+        -> {"lidar_bev": [B,290,400,720], "map_bev": [B,9,400,720]} float32 CUDA tensors, i.e. exactly
+           what collate_fn stacks and train_vit.py:154-159 moves to the device and feeds to the model.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import augment as _aug
+from . import bev_ops, map_ops, pose
+from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LIDAR_SWEEPS, MAP_CHANNELS)
+
+
+def _pinned(arr: np.ndarray) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+@dataclasses.dataclass
+class FrameBatch:
+    """Host-side (pinned) packed batch."""
+    points4: torch.Tensor        # float32 [N,4]
+    sweep_offsets: torch.Tensor  # int32 [B*S+1]
+    rel_tf: torch.Tensor         # float64 [B*S,16]
+    ego_T: torch.Tensor          # float64 [B,9]
+    map_ids: np.ndarray          # int64 [B]  (-1 = no map)
+    num_frames: int
+    num_sweeps: int
+    max_sweep_points: int
+
+    @property
+    def num_points(self) -> int:
+        return int(self.points4.shape[0])
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(self.points4.numel() * 4 + self.sweep_offsets.numel() * 4 + self.rel_tf.numel() * 8 + self.ego_T.numel() * 8)
+
+    @staticmethod
+    def pack(frames: Sequence, num_sweeps: int = LIDAR_SWEEPS, map_ids: Optional[Sequence[int]] = None) -> "FrameBatch":
+        """frames: objects with points4 [n,4] f32, sweep_offsets [s+1], sweep_poses [s,7], current_pose [7]
+        (e.g. synthetic.Frame).  Sweeps beyond ``num_sweeps`` are an error, as in the reference (utils.py:102)."""
+        B, S = len(frames), int(num_sweeps)
+        counts = np.zeros((B, S), np.int64)
+        rel = np.tile(np.eye(4), (B, S, 1, 1))
+        ego = np.tile(np.eye(3), (B, 1, 1))
+        for b, f in enumerate(frames):
+            ns = len(f.sweep_offsets) - 1
+            if ns > S:
+                raise IndexError(f"frame {b}: {ns} sweeps but num_sweeps={S}")
+            counts[b, :ns] = np.diff(f.sweep_offsets)
+            rel[b, :ns] = pose.sweep_rel_transforms(f.current_pose, f.sweep_poses)      # dataset.py:285-339
+            cp = np.asarray(f.current_pose, np.float64)
+            ego[b] = pose.map_matrix_from_pose(cp[0], cp[1], cp[3:7])                   # utils.py:121-129
+        off = np.zeros(B * S + 1, np.int64)
+        off[1:] = np.cumsum(counts.reshape(-1))
+        if off[-1] >= 2 ** 31:
+            raise ValueError("more than 2^31 points in one batch")
+        pts = np.concatenate([np.asarray(f.points4, np.float32).reshape(-1, 4) for f in frames], 0) if B else np.zeros((0, 4), np.float32)
+        ids = np.full(B, -1, np.int64) if map_ids is None else np.asarray(map_ids, np.int64)
+        return FrameBatch(_pinned(pts), _pinned(off.astype(np.int32)), _pinned(rel.reshape(B * S, 16)),
+                          _pinned(ego.reshape(B, 9)), ids, B, S, int(counts.max()) if B else 0)
+
+
+class BevGenerator:
+    """Owns the device-side state (map table, workspaces) and turns FrameBatches into model inputs."""
+
+    def __init__(self, map_table: Optional[map_ops.MapTable] = None, algo: int = bev_ops.ALGO_ATOMIC,
+                 device: Optional[torch.device] = None) -> None:
+        self.device = device or bev_ops._require_cuda()
+        self.map_table = map_table
+        self.algo = algo
+        self._scratch = {}
+
+    def _buf(self, key, shape) -> torch.Tensor:
+        t = self._scratch.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=torch.float32, device=self.device)
+            self._scratch[key] = t
+        return t
+
+    def upload(self, batch: FrameBatch) -> dict:
+        """Async H2D of the packed batch (pinned -> device) on the current stream."""
+        d = self.device
+        return {"points4": batch.points4.to(d, non_blocking=True), "sweep_offsets": batch.sweep_offsets.to(d, non_blocking=True),
+                "rel_tf": batch.rel_tf.to(d, non_blocking=True), "ego_T": batch.ego_T.to(d, non_blocking=True)}
+
+    def generate(self, batch: FrameBatch, aug: Optional[Sequence[_aug.AugParams]] = None, *, dev: Optional[dict] = None,
+                 with_map: bool = True, out_lidar: Optional[torch.Tensor] = None,
+                 out_map: Optional[torch.Tensor] = None) -> dict:
+        """Returns {"lidar_bev", "map_bev"} CUDA tensors.  ``aug`` = one AugParams per frame (train time):
+        flip / dropout of frames that need no resampling are fused into generation (zero extra bytes); if any
+        frame rotates or scales, the batch goes through the single fused gather kernel."""
+        B, S = batch.num_frames, batch.num_sweeps
+        dv = dev if dev is not None else self.upload(batch)
+        gather = aug is not None and any(p.needs_gather for p in aug)
+        flip = rects = cnt = None
+        if aug is not None:
+            if len(aug) != B:
+                raise ValueError("one AugParams per frame")
+            flip, rects, cnt = _aug.fusion_arrays(aug)
+        lshape = (B, S * LIDAR_HEIGHT_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
+        mshape = (B, MAP_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
+        gen_l = self._buf("gen_l", lshape) if gather else out_lidar
+        lid = bev_ops.lidar_bev_from_sweeps(dv["points4"], dv["sweep_offsets"], dv["rel_tf"], B, S,
+                                            max_sweep_points=batch.max_sweep_points, flip=flip, drop_rects=rects,
+                                            drop_counts=cnt, out=gen_l, algo=self.algo)
+        mp = None
+        if with_map:
+            if self.map_table is None or (batch.map_ids < 0).any():
+                raise ValueError("with_map=True needs a MapTable and a map id per frame")
+            gen_m = self._buf("gen_m", mshape) if gather else out_map
+            mp = map_ops.rasterize_maps(self.map_table, batch.map_ids, dv["ego_T"], flip=flip, drop_rects=rects,
+                                        drop_counts=cnt, out=gen_m)
+        if gather:
+            # flip / dropout of the frames that need no resampling were already fused above: identity for them here
+            gp = [p if p.needs_gather else _aug.AugParams() for p in aug]
+            lid = _aug.augment_grid(lid, gp, out=out_lidar)
+            if mp is not None:
+                mp = _aug.augment_grid(mp, gp, out=out_map)
+        return {"lidar_bev": lid, "map_bev": mp}
