@@ -1,0 +1,97 @@
+"""CPU: host-side logic of the product (no kernels): map pre-parse, batch packing, parameter packing, sharding."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def bg():
+    import bevgen_b200
+    return bevgen_b200
+
+
+def test_flat_map_skips_unusable_entries(bg):
+    md = {"lane_segments": {
+        "a": {"left_lane_boundary": [{"x": 1.0, "y": 2.0}, "junk", {"x": 3.0}, {"x": 4.0, "y": 5.0, "z": 9}],
+              "right_lane_boundary": [], "is_intersection": True, "lane_type": "BUS",
+              "left_lane_mark_type": "SOLID_YELLOW", "right_lane_mark_type": "NONE"},
+        "b": {"left_lane_boundary": [None], "right_lane_boundary": [{"x": 0.0, "y": 0.0}, {"x": 1.0, "y": 1.0}]}},
+        "pedestrian_crossings": {"c": {"polygon": [{"x": 0, "y": 0}, {"x": 1, "y": 0}, {"x": 1, "y": 1}]}, "d": {"edge1": []}}}
+    fm = bg.maps.parse_map_dict(md)
+    assert fm.verts.tolist() == [[1, 2], [4, 5], [0, 0], [1, 1], [0, 0], [1, 0], [1, 1]]
+    assert fm.pl_off.tolist() == [0, 2, 4, 7]
+    assert fm.lanes.tolist() == [[0, -1, 1 | 2 | (8 << 4), 0], [-1, 1, 0, 0]]
+    assert fm.cws.tolist() == [2]
+    assert fm.num_prims == 3 and fm.max_polyline_len() == 3
+    assert bg.maps.parse_map_dict({}).num_prims == 0
+    too_long = {"lane_segments": {"a": {"left_lane_boundary": [{"x": i, "y": 0} for i in range(1025)]}}}
+    with pytest.raises(ValueError):
+        bg.maps.parse_map_dict(too_long)
+
+
+def test_frame_batch_pack(bg):
+    frames = [bg.synthetic.frame_c2(0, n=50, S=10), bg.synthetic.frame_c1(0, n=33), bg.synthetic.frame_c2(1, n=7, S=4)]
+    fb = bg.FrameBatch.pack(frames, 10)
+    off = fb.sweep_offsets.numpy()
+    assert fb.num_frames == 3 and fb.num_sweeps == 10 and off.shape == (31,)
+    assert fb.num_points == 500 + 33 + 28 and fb.max_sweep_points == 50
+    assert np.diff(off).tolist() == [50] * 10 + [33] + [0] * 9 + [7] * 4 + [0] * 6
+    rel = fb.rel_tf.numpy().reshape(3, 10, 4, 4)
+    assert np.array_equal(rel[0], frames[0].rel_tf) and np.array_equal(rel[2, :4], frames[2].rel_tf)
+    assert np.array_equal(rel[1, 5], np.eye(4))
+    with pytest.raises(IndexError):
+        bg.FrameBatch.pack(frames, 3)
+
+
+def test_aug_param_struct_layout(bg):
+    from bevgen_b200 import _native
+    assert ctypes.sizeof(_native.AugParams) == 152          # 6*8 + 8 + 4*4 + 20*4 (include/bevgen.h)
+    p = bg.AugParams(flip=True, angle_deg=5.0, scale=0.97, rects=[(1, 2, 20, 30), (3, 4, 25, 35)])
+    raw = bg.augment.pack_params([bg.AugParams(), p])
+    assert raw.shape == (304,)
+    s = _native.AugParams.from_buffer_copy(raw[152:].tobytes())
+    assert (s.do_flip, s.do_rotate, s.do_scale, s.n_rects) == (1, 1, 1, 2)
+    assert list(s.rects[:8]) == [1, 2, 20, 30, 3, 4, 25, 35] and s.scale == 0.97
+    mi = bg.augment.invert_affine_2x3(bg.augment.rotation_matrix_2d(5.0)).reshape(6)
+    assert list(s.minv) == mi.tolist()
+    z = _native.AugParams.from_buffer_copy(raw[:152].tobytes())
+    assert (z.do_flip, z.do_rotate, z.do_scale, z.n_rects) == (0, 0, 0, 0)
+    flip, rects, cnt = bg.augment.fusion_arrays([bg.AugParams(flip=True, rects=[(5, 6, 20, 20)]), p])
+    assert flip.tolist() == [1, 0] and cnt.tolist() == [1, 0] and rects[0, 0].tolist() == [5, 6, 20, 20]
+
+
+def test_draw_aug_params_ranges(bg):
+    random.seed(99)
+    seen = set()
+    for _ in range(400):
+        p = bg.draw_aug_params(random)
+        seen.add((p.flip, p.angle_deg is not None, p.scale is not None, bool(p.rects)))
+        assert p.angle_deg is None or -15.0 <= p.angle_deg <= 15.0
+        assert p.scale is None or 0.95 <= p.scale <= 1.05
+        assert len(p.rects) <= 5
+        for y0, x0, ph, pw in p.rects:
+            assert 20 <= ph <= 50 and 20 <= pw <= 50 and 0 <= y0 <= 400 - ph and 0 <= x0 <= 720 - pw
+    assert len(seen) == 16
+
+
+def test_shard_range(bg):
+    from bevgen_b200 import sharding
+    for n in (0, 1, 7, 256):
+        for w in (1, 2, 3, 8):
+            got = [i for r in range(w) for i in sharding.shard_range(n, r, w)]
+            assert got == list(range(n))
+            sizes = [len(sharding.shard_range(n, r, w)) for r in range(w)]
+            assert max(sizes) - min(sizes) <= 1
+    assert sharding.gather_stats({"a": 1.5}) == {"a": [1.5]}
+
+
+def test_no_cuda_means_loud_failure(bg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        bg.create_intentnet_lidar_bev([np.zeros((3, 3))], [np.ones(3, np.float32)])
+    with pytest.raises(RuntimeError):
+        bg.transform_points(np.zeros((3, 3), np.float32), np.eye(4))

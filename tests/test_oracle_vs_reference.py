@@ -1,0 +1,150 @@
+"""CPU, build container only: the C oracle and the numpy port equal the UNMODIFIED reference functions executed
+live (read-only from /root/reference).  Skipped where the reference is absent (e.g. the GPU box), where the
+committed golden vectors (tests/test_golden_cpu.py) carry the pin instead."""
+import json
+import random
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co, ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference sources not present")
+
+
+@pytest.fixture(scope="module")
+def u():
+    return ref_loader.utils()
+
+
+@pytest.fixture(scope="module")
+def bg():
+    import bevgen_b200
+    return bevgen_b200
+
+
+def test_constants_match_reference(bg):
+    c = ref_loader.load("constants")
+    k = bg.constants
+    for name in ("GRID_HEIGHT_PX", "GRID_WIDTH_PX", "VOXEL_SIZE_M", "BEV_PIXEL_OFFSET_X", "BEV_PIXEL_OFFSET_Y", "Z_MIN",
+                 "Z_MAX", "LIDAR_HEIGHT_CHANNELS", "LIDAR_SWEEPS", "LIDAR_TOTAL_CHANNELS", "MAP_CHANNELS", "INTENTIONS_MAP"):
+        assert getattr(k, name) == getattr(c, name), name
+    oc = co.constants()
+    assert (oc["GRID_H"], oc["GRID_W"], oc["VOXEL"], oc["Z_SPAN"]) == (400, 720, c.VOXEL_SIZE_M, c.Z_MAX - c.Z_MIN)
+
+
+def test_transform_and_lidar(u, bg):
+    f = bg.synthetic.frame_c2(3, n=20_000)
+    pl, il, pl_o = [], [], []
+    for s in range(10):
+        sw = f.sweep(s)
+        a = u.transform_points(sw[:, :3], f.rel_tf[s])
+        b = co.transform_points(sw[:, :3], f.rel_tf[s])
+        assert np.array_equal(a, b)
+        pl.append(a); il.append(sw[:, 3].copy())
+    pl[4] = None; il[4] = None
+    ref = u.create_intentnet_lidar_bev(pl, il)
+    assert np.array_equal(ref, co.lidar_bev(pl, il))
+    off2 = f.sweep_offsets.copy()
+    keep = np.ones(f.num_points, bool); keep[off2[4]:off2[5]] = False
+    off3 = off2.copy(); off3[5:] -= off2[5] - off2[4]
+    assert np.array_equal(ref, co.lidar_bev_fused(f.points4[keep], off3, f.rel_tf, 10))
+    # contention config
+    g = bg.synthetic.frame_c4(1, n=10_000)
+    pl = [u.transform_points(g.sweep(s)[:, :3], g.rel_tf[s]) for s in range(10)]
+    il = [g.sweep(s)[:, 3].copy() for s in range(10)]
+    assert np.array_equal(u.create_intentnet_lidar_bev(pl, il), co.lidar_bev_fused(g.points4, g.sweep_offsets, g.rel_tf, 10))
+
+
+def test_pose_prep_matches_dataset_code(bg):
+    """pose.py vs the literal numpy/scipy sequence of dataset.py:293-301, :331-339 (restated in numpy_port)."""
+    from oracle import numpy_port as npp
+    f = bg.synthetic.frame_c3(2, n=10, S=6)
+    ours = bg.pose.sweep_rel_transforms(f.current_pose, f.sweep_poses)
+    theirs = np.stack(npp.rel_transforms(f.current_pose, f.sweep_poses))
+    assert np.array_equal(ours, theirs)
+
+
+def test_map_raster(u, bg, tmp_path):
+    md = bg.synthetic.synthetic_map(seed=5, rows=14, cols=11, n_cross=9)
+    path = bg.synthetic.write_map_json(md, tmp_path / "m.json")
+    flat = co.flatten_map(md)
+    fm = bg.maps.parse_map_dict(md)
+    for k in ("verts", "pl_off", "lanes", "cws"):
+        assert np.array_equal(getattr(fm, k), flat[k]), k
+    import pandas as pd
+    from scipy.spatial.transform import Rotation as R
+    from oracle import numpy_port as npp
+    rng = np.random.default_rng(2)
+    for _ in range(5):
+        tx, ty = 1500 + rng.uniform(-80, 80), -700 + rng.uniform(-80, 80)
+        q = R.from_euler("xyz", [0.0, 0.01, rng.uniform(-3, 3)]).as_quat()
+        ser = pd.Series(dict(tx_m=tx, ty_m=ty, tz_m=0.0, qx=q[0], qy=q[1], qz=q[2], qw=q[3]))
+        ref = u.rasterize_map_ego_centric(path, ser)
+        T3 = bg.pose.map_matrix_from_pose(tx, ty, q)
+        assert np.array_equal(T3, u.get_ego_centric_transform_matrix(np.array([tx, ty]), R.from_quat(q).as_euler("xyz")[2]))
+        assert np.array_equal(ref, co.map_raster_flat(flat, T3))
+        assert np.array_equal(ref, npp.map_raster(path, ser))
+    xy = np.stack([1500 + rng.uniform(-90, 90, 3000), -700 + rng.uniform(-90, 90, 3000)], 1)
+    assert np.array_equal(u.world_to_bev_pixel(xy, T3), co.world_to_bev_pixel(xy, T3))
+
+
+def test_cv2_line_and_fill_restatement():
+    import cv2
+    rng = np.random.default_rng(4)
+    for t in range(1500):
+        n = int(rng.integers(3, 30))
+        c = np.array([rng.integers(0, 720), rng.integers(0, 400)])
+        pts = c + rng.integers(-35, 36, (n, 2)) if t % 2 else np.stack([rng.integers(0, 720, n), rng.integers(0, 400, n)], 1)
+        pts[:, 0] = np.clip(pts[:, 0], 0, 719); pts[:, 1] = np.clip(pts[:, 1], 0, 399)
+        a = np.zeros((400, 720), np.uint8); b = np.zeros_like(a)
+        if t % 3:
+            cv2.fillPoly(a, [pts.reshape(-1, 1, 2).astype(np.int64)], color=1); co.fill_poly(b, pts)
+        else:
+            cv2.polylines(a, [pts.reshape(-1, 1, 2).astype(np.int64)], False, 1, 1); co.polyline(b, pts)
+        assert np.array_equal(a, b), t
+
+
+def test_augmentation_ops(u, bg):
+    import cv2
+    from oracle import numpy_port as npp
+    rng = np.random.default_rng(8)
+    g = np.zeros((3, 400, 720), np.float32)
+    ii = rng.integers(0, g.size, 9000); g.reshape(-1)[ii] = rng.integers(1, 256, ii.size)
+    d = rng.uniform(0, 255, (1, 400, 720)).astype(np.float32)
+    old_ipp = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        for ang in (7.3, -15.0, 0.001):
+            for src in (g, d):
+                lo, mo = npp.augment(src, src[:1], angle_deg=ang)
+                assert np.array_equal(lo, co.rotate(src, ang))
+                assert np.array_equal(bg.augment.rotation_matrix_2d(ang), cv2.getRotationMatrix2D((360.0, 200.0), ang, 1.0))
+                assert np.array_equal(bg.augment.invert_affine_2x3(bg.augment.rotation_matrix_2d(ang)),
+                                      co.invert_affine(co.rotation_matrix(ang)))
+        for s in (0.95, 0.9731, 1.0, 1.0009, 1.05):
+            for src in (g, d):
+                lo, _ = npp.augment(src, src[:1], scale=s)
+                assert np.array_equal(lo, co.scale(src, s)), s
+        lo, _ = npp.augment(g, g[:1], flip=True, rects=[(10, 20, 30, 40), (390, 700, 50, 50)])
+        want = co.flip_w(g); co.dropout(want, [(10, 20, 30, 40), (390, 700, 50, 50)])
+        assert np.array_equal(lo, want)
+    finally:
+        cv2.ipp.setUseIPP(old_ipp)
+    # default (IPP) resize stays within the stated tolerance of the restatement
+    lo, _ = npp.augment(d, d[:1], scale=1.0288)
+    assert np.abs(lo - co.scale(d, 1.0288)).max() <= 2.5e-2
+
+
+def test_rng_draw_order_matches_reference(u, bg):
+    """draw_aug_params consumes Python's global RNG exactly like augment_bev's four random_* calls."""
+    import torch
+    lid = np.zeros((1, 400, 720), np.float32); mp = np.zeros((1, 400, 720), np.float32)
+    gt = {"boxes_xywha": torch.zeros((0, 5)), "intentions": torch.zeros((0,), dtype=torch.long)}
+    for seed in range(40):
+        random.seed(seed)
+        u.augment_bev(lid, mp, gt)
+        state_ref = random.getstate()
+        random.seed(seed)
+        bg.augment.draw_aug_params(random)
+        assert random.getstate() == state_ref, seed
