@@ -30,7 +30,9 @@ from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LI
 #   ATOMIC         TMA zero-fill kernel + one global-atomicMax scatter kernel            (hand-written only)
 #   FUSED[_DEDUPE] one persistent cooperative kernel: TMA zero fill + dependent atomic scatter
 #   MEMSET_ATOMIC  cudaMemsetAsync + the same scatter kernel (library fill, kept as a comparison point)
-ALGO_TILED, ALGO_ATOMIC, ALGO_FUSED, ALGO_FUSED_DEDUPE, ALGO_MEMSET_ATOMIC = 0, 1, 2, 3, 4
+#   TICKET         ONE ordinary launch: ticket-ordered CTAs, per sweep 2320 TMA zero-fill CTAs then the scatter CTAs
+#                  (atomics land on L2-resident lines)
+ALGO_TILED, ALGO_ATOMIC, ALGO_FUSED, ALGO_FUSED_DEDUPE, ALGO_MEMSET_ATOMIC, ALGO_TICKET = 0, 1, 2, 3, 4, 5
 MAX_DROP_RECTS = 5
 
 
@@ -166,13 +168,15 @@ def lidar_bev_from_ego_points(points3, intensity, sweep_offsets, num_frames: int
     return out
 
 
-def fused_spin_timeout_flag(num_frames: int, num_sweeps: int = LIDAR_SWEEPS) -> int:
-    """Debug/test hook: 1 if the fused kernel's bounded dependency spin ever timed out in the last
-    ALGO_FUSED call on this device (results would then be incomplete); synchronises the stream."""
+def fused_spin_timeout_flag(num_frames: int, num_sweeps: int = LIDAR_SWEEPS, algo: int = 2) -> int:
+    """Debug/test hook: 1 if a bounded dependency spin of the last ALGO_FUSED / ALGO_TICKET call on this device
+    timed out (the result would then be incomplete).  Synchronises the stream."""
     device = _require_cuda()
     ws = workspace.get("lidar", 0, device)
     torch.cuda.current_stream().synchronize()
-    return int(ws[: (num_frames * num_sweeps + 1) * 4].view(torch.int32)[num_frames * num_sweeps].item())
+    n = num_frames * num_sweeps
+    idx = n + 1 if algo == ALGO_TICKET else 2 * n          # workspace layouts of csrc/lidar.cu
+    return int(ws[: (idx + 1) * 4].view(torch.int32)[idx].item())
 
 
 # =========================================================================== reference signatures

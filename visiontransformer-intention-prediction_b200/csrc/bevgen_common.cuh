@@ -65,17 +65,18 @@ __device__ __forceinline__ void xform_point(const double* __restrict__ T, double
     oz = __fma_rn(T[11], 1.0, __fma_rn(T[10], z, __fma_rn(T[9], y, __fma_rn(T[8], x, 0.0))));
 }
 
-// utils.py:80-95 evaluated literally (three IEEE float64 divisions).  Returns false when masked out.
-static __device__ __noinline__ bool lidar_voxel_exact(double x, double y, double z, int& py, int& px, int& zb) {
+// utils.py:80-95 evaluated literally (three IEEE float64 divisions).  Returns the voxel packed as
+// (zb << 20) | (py << 10) | px, or -1 when the point is masked out (utils.py:83-87).  Kept out of line (it is the
+// rare path) and free of reference parameters so that nothing is forced into local memory.
+static __device__ __noinline__ int lidar_voxel_exact(double x, double y, double z) {
     const double fx = floor(__dadd_rn(kOffX, __ddiv_rn(y, kVoxel)));   // utils.py:80
     const double fy = floor(__dsub_rn(kOffY, __ddiv_rn(x, kVoxel)));   // utils.py:81
     // NaN / +-inf / out-of-range fail these compares, as the reference's INT_MIN cast does
-    if (!(fx >= 0.0 && fx < (double)kW && fy >= 0.0 && fy < (double)kH && z >= kZMin && z < kZMax)) return false;
+    if (!(fx >= 0.0 && fx < (double)kW && fy >= 0.0 && fy < (double)kH && z >= kZMin && z < kZMax)) return -1;
     const double fz = floor(__dmul_rn(__ddiv_rn(__dsub_rn(z, kZMin), kZSpan), (double)kZ));   // utils.py:94
     int b = (int)fz;
     b = b < 0 ? 0 : (b > kZ - 1 ? kZ - 1 : b);                                                // utils.py:95
-    px = (int)fx; py = (int)fy; zb = b;
-    return true;
+    return (b << 20) | ((int)fy << 10) | (int)fx;
 }
 
 // Same result, bit for bit, without the divisions on the common path.
@@ -93,12 +94,15 @@ __device__ __forceinline__ bool lidar_voxel(double x, double y, double z, int& p
     const double fx = floor(tx), fy = floor(ty), fz = floor(tz);
     constexpr double kEps = 1e-6;
     const double dx = __dsub_rn(tx, fx), dy = __dsub_rn(ty, fy), dz = __dsub_rn(tz, fz);
-    if (dx < kEps || dx > 1.0 - kEps || dy < kEps || dy > 1.0 - kEps || dz < kEps || dz > 1.0 - kEps)
-        return lidar_voxel_exact(x, y, z, py, px, zb);
-    if (!(fx >= 0.0 && fx < (double)kW && fy >= 0.0 && fy < (double)kH)) return false;
-    int b = (int)fz;
-    b = b > kZ - 1 ? kZ - 1 : b;
-    px = (int)fx; py = (int)fy; zb = b;
+    int packed;
+    if (dx < kEps || dx > 1.0 - kEps || dy < kEps || dy > 1.0 - kEps || dz < kEps || dz > 1.0 - kEps) {
+        packed = lidar_voxel_exact(x, y, z);
+    } else {
+        const int b = min((int)fz, kZ - 1);
+        packed = (fx >= 0.0 && fx < (double)kW && fy >= 0.0 && fy < (double)kH) ? ((b << 20) | ((int)fy << 10) | (int)fx) : -1;
+    }
+    if (packed < 0) return false;
+    px = packed & 1023; py = (packed >> 10) & 1023; zb = packed >> 20;
     return true;
 }
 

@@ -263,22 +263,29 @@ __global__ void __launch_bounds__(kRasterThreads, 1) k_raster_store(const uint2*
 // One cooperative launch for the whole batch; warp-specialised CTAs:
 //   producer warps (kProducers, lane 0 only): walk the fill chunks g = 0 .. B*S*1160-1; each chunk is ONE TMA
 //       bulk store of an immutable all-zero shared-memory tile (kFillBytes) to out + g*kFillBytes -- no LSU
-//       traffic, no registers.  When the store has completed (bulk wait_group), the producer publishes it:
-//       proxy fence + __threadfence + atomicAdd(done[sweep of g]).  Producers never wait on anything else,
-//       so the fill stream runs at TMA/HBM speed from the first to the last byte of the batch.
-//   consumer warps: walk the scatter chunks (1024 points each, sweep-major).  A sweep region (29 channels =
-//       33.4 MB = 1160 fill chunks) may only be scattered into after ALL its fill chunks have landed:
-//       ld.acquire spin on done[js] == 1160 (bounded).  Then transform, bin and RED.MAX into out.
-// Scatter trails the fill front by about one sweep region, so its atomics hit lines that are still dirty in
-// the 126 MB L2 and cost no DRAM read-modify-write.  All CTAs are co-resident (cooperative launch) and
-// producers are independent of consumers, hence no deadlock.
+//       traffic, no registers.  When the store has completed (bulk wait_group) the producer publishes it:
+//       proxy fence + __threadfence + atomicAdd(done[sweep of g]).
+//   consumer warps: walk the scatter chunks (kScatChunk points each, sweep-major).  A sweep region (29 channels
+//       = 33.4 MB = 1160 fill chunks) may only be scattered into after ALL its fill chunks have landed:
+//       ld.acquire spin on done[js] == 1160.  Then transform, bin and RED.MAX into out, and publish
+//       scat[js] += 1 per finished chunk.
+//   flow control: a producer may fill sweep j only once sweep j - kWindow has been completely scattered
+//       (scat[j - kWindow] == chunks per sweep).  This keeps the fill front at most kWindow sweep regions
+//       (66.8 MB) ahead of the scatter front, so the atomics hit lines that are still dirty in the 126 MB L2
+//       (measured: 61 G RED/s on L2-resident lines vs 22 G RED/s when every RED has to fetch its sector from
+//       HBM, tools/redbench.cu).
+// Dependencies are acyclic (fill j <- scatter j-2 <- fill j-2 <- ...), producers publish everything they hold
+// before they block, all CTAs are co-resident (cooperative launch): no deadlock.  Every spin is bounded.
 constexpr int kFillRows = 10;
 constexpr int kFillBytes = kFillRows * kRowBytes;                    // 28 800 B
 constexpr int kFillPerSweep = kZ * kH / kFillRows;                   // 1160 chunks per (frame, sweep)
 constexpr int kProducers = 4;                                        // producer warps per CTA
 constexpr int kConsumerThreads = 128;
 constexpr int kFusedThreads = kProducers * 32 + kConsumerThreads;    // 256
-constexpr int kScatItems = kBinChunk / kConsumerThreads;             // 8 points per consumer thread per chunk
+constexpr int kScatItems = 4;                                        // points per consumer thread per chunk
+constexpr int kScatChunk = kConsumerThreads * kScatItems;            // 512 points
+constexpr int kWindow = 2;
+constexpr unsigned kSpinLimit = 20000000u;
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;
@@ -287,9 +294,20 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kConsumerThreads) : "memory"); }
 
+// returns false on timeout (never hang the GPU)
+__device__ __forceinline__ bool spin_until(const uint32_t* ctr, uint32_t target, uint32_t* err_flag) {
+    unsigned spins = 0;
+    while (ld_acquire_u32(ctr) < target) {
+        __nanosleep(64);
+        if (++spins > kSpinLimit) { atomicExch(err_flag, 1u); return false; }
+    }
+    return true;
+}
+
 template <int MODE, bool DEDUPE>
 __global__ void __launch_bounds__(kFusedThreads) k_fill_scatter(LidarIn in, uint32_t* __restrict__ out,
-                                                                uint32_t* __restrict__ done, uint32_t* __restrict__ err_flag,
+                                                                uint32_t* __restrict__ done, uint32_t* __restrict__ scat,
+                                                                uint32_t* __restrict__ err_flag,
                                                                 int num_sweeps_total, int chunks_per_sweep) {
     extern __shared__ __align__(128) unsigned char zero_tile[];
     __shared__ double sT[12];
@@ -307,23 +325,30 @@ __global__ void __launch_bounds__(kFusedThreads) k_fill_scatter(LidarIn in, uint
         const long long total_fill = (long long)num_sweeps_total * kFillPerSweep;
         const long long stride = (long long)gridDim.x * kProducers;
         long long prev = -1;
-        for (long long g = (long long)blockIdx.x * kProducers + warp; g < total_fill; g += stride) {
-            bulk_store_s2g(reinterpret_cast<unsigned char*>(out) + g * kFillBytes, zero_tile, kFillBytes);
-            bulk_commit();
-            if (prev >= 0) {                 // one store stays in flight while the previous one is published
-                bulk_wait_all<1>();
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence();
-                atomicAdd(&done[prev / kFillPerSweep], 1u);
-            }
-            prev = g;
-        }
-        if (prev >= 0) {
-            bulk_wait_all<0>();
+        int cleared = kWindow - 1;           // sweeps <= cleared may be filled without asking
+        bool ok = true;
+        auto publish_prev = [&](bool all) {
+            if (prev < 0) return;
+            if (all) bulk_wait_all<0>(); else bulk_wait_all<1>();
             asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
             atomicAdd(&done[prev / kFillPerSweep], 1u);
+            prev = -1;
+        };
+        for (long long g = (long long)blockIdx.x * kProducers + warp; g < total_fill && ok; g += stride) {
+            const int j = (int)(g / kFillPerSweep);
+            if (j > cleared) {               // flow control: sweep j - kWindow must be fully scattered
+                publish_prev(true);          // never block while holding an unpublished chunk
+                ok = spin_until(&scat[j - kWindow], (uint32_t)chunks_per_sweep, err_flag);
+                cleared = j;
+            }
+            bulk_store_s2g(reinterpret_cast<unsigned char*>(out) + g * kFillBytes, zero_tile, kFillBytes);
+            bulk_commit();
+            const long long mine = g;
+            publish_prev(false);             // one store stays in flight while the previous one is published
+            prev = mine;
         }
+        publish_prev(true);
         return;
     }
 
@@ -331,80 +356,158 @@ __global__ void __launch_bounds__(kFusedThreads) k_fill_scatter(LidarIn in, uint
     const int ctid = tid - kProducers * 32;
     const long long total_scat = (long long)num_sweeps_total * chunks_per_sweep;
     int cur_bs = -1;                 // sweep whose constants are in shared memory
-    int ready_bs = -1;               // highest sweep known to be completely filled (monotone in hs order)
+    int ready_bs = -1;               // sweep known to be completely filled
     for (long long hs = blockIdx.x; hs < total_scat; hs += gridDim.x) {
         const int bs = (int)(hs / chunks_per_sweep);
         const int c = (int)(hs - (long long)bs * chunks_per_sweep);
         const int beg = in.sweep_off[bs], end = in.sweep_off[bs + 1];
-        const long long chunk0 = (long long)beg + (long long)c * kBinChunk;
-        if (chunk0 >= end) continue;                         // uniform: ragged sweep, nothing in this chunk
-        if (bs != ready_bs) {
-            if (ctid == 0) {
-                unsigned spins = 0;
-                while (ld_acquire_u32(&done[bs]) < (uint32_t)kFillPerSweep) {
-                    __nanosleep(100);
-                    if (++spins > 20000000u) { s_ok = 0; atomicExch(err_flag, 1u); break; }   // never hang the GPU
+        const long long chunk0 = (long long)beg + (long long)c * kScatChunk;
+        if (chunk0 < end) {
+            // issue the point loads first: their latency overlaps the wait for the fill
+            RawPoint<MODE> raw[kScatItems];
+#pragma unroll
+            for (int it = 0; it < kScatItems; ++it) {
+                const long long i = chunk0 + it * kConsumerThreads + ctid;
+                raw[it] = load_point<MODE>(in, i, i < end);
+            }
+            if (bs != ready_bs) {
+                if (ctid == 0 && !spin_until(&done[bs], (uint32_t)kFillPerSweep, err_flag)) s_ok = 0;
+                consumer_sync();                                 // also orders the previous chunk's sT readers
+                ready_bs = bs;
+            }
+            if (bs != cur_bs) {
+                if (MODE == 0 && ctid < 12) sT[ctid] = in.rel_tf[(size_t)bs * 16 + ctid];
+                const int b0 = bs / in.S;
+                int nr = in.nrects ? in.nrects[b0] : 0;
+                nr = nr > kMaxRects ? kMaxRects : nr;
+                if (ctid < 4 * nr) sRect[ctid] = in.rects[(size_t)b0 * kMaxRects * 4 + ctid];
+                cur_bs = bs;
+                consumer_sync();
+            }
+            const int b = bs / in.S;
+            int nrect = in.nrects ? in.nrects[b] : 0;
+            nrect = nrect > kMaxRects ? kMaxRects : nrect;
+            const bool flip = in.flip ? (in.flip[b] != 0) : false;
+            if (s_ok) {
+                uint32_t* region = out + (size_t)bs * kZ * kPlane;
+#pragma unroll
+                for (int it = 0; it < kScatItems; ++it) {
+                    const long long i = chunk0 + it * kConsumerThreads + ctid;
+                    int row = 0; uint32_t cell = 0, bits = 0;
+                    const bool ok = (i < end) && point_record<MODE>(raw[it], sT, flip, sRect, nrect, row, cell, bits);
+                    const uint32_t zb = cell / kW, px = cell - zb * kW;
+                    const uint32_t vox = (zb * kH + (uint32_t)row) * kW + px;
+                    if (DEDUPE) {      // warp-aggregated: one RED per distinct voxel per warp
+                        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ok ? vox : 0xFFFFFFFFu);
+                        const uint32_t m = __reduce_max_sync(peers, bits);
+                        if (ok && lane == __ffs(peers) - 1) atomicMax(region + vox, m);
+                    } else if (ok) {
+                        atomicMax(region + vox, bits);
+                    }
                 }
             }
-            consumer_sync();                                 // also orders the previous chunk's sT readers
-            ready_bs = bs;
+            consumer_sync();                                     // every thread's REDs are issued
         }
-        if (bs != cur_bs) {
-            if (MODE == 0 && ctid < 12) sT[ctid] = in.rel_tf[(size_t)bs * 16 + ctid];
-            const int b0 = bs / in.S;
-            int nr = in.nrects ? in.nrects[b0] : 0;
-            nr = nr > kMaxRects ? kMaxRects : nr;
-            if (ctid < 4 * nr) sRect[ctid] = in.rects[(size_t)b0 * kMaxRects * 4 + ctid];
-            cur_bs = bs;
-            consumer_sync();
-        }
-        const int b = bs / in.S;
-        int nrect = in.nrects ? in.nrects[b] : 0;
-        nrect = nrect > kMaxRects ? kMaxRects : nrect;
-        const bool flip = in.flip ? (in.flip[b] != 0) : false;
-        if (!s_ok) continue;
-        uint32_t* region = out + (size_t)bs * kZ * kPlane;
-        RawPoint<MODE> raw[kScatItems];
-#pragma unroll
-        for (int it = 0; it < kScatItems; ++it) {
-            const long long i = chunk0 + it * kConsumerThreads + ctid;
-            raw[it] = load_point<MODE>(in, i, i < end);
-        }
-#pragma unroll
-        for (int it = 0; it < kScatItems; ++it) {
-            const long long i = chunk0 + it * kConsumerThreads + ctid;
-            int row = 0; uint32_t cell = 0, bits = 0;
-            const bool ok = (i < end) && point_record<MODE>(raw[it], sT, flip, sRect, nrect, row, cell, bits);
-            const uint32_t zb = cell / kW, px = cell - zb * kW;
-            const uint32_t vox = (zb * kH + (uint32_t)row) * kW + px;
-            if (DEDUPE) {      // warp-aggregated: one RED per distinct voxel per warp
-                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ok ? vox : 0xFFFFFFFFu);
-                const uint32_t m = __reduce_max_sync(peers, bits);
-                if (ok && lane == __ffs(peers) - 1) atomicMax(region + vox, m);
-            } else if (ok) {
-                atomicMax(region + vox, bits);
-            }
-        }
+        if (ctid == 0) atomicAdd(&scat[bs], 1u);                 // publish: this chunk of sweep bs is scattered
     }
 }
 
-// ---- zero fill by TMA: every CTA bulk-stores an immutable all-zero shared-memory tile -------------------
-// (cp.async.bulk.global.shared::cta, kFillBytes per store, kFillDepth stores in flight per CTA; no LSU traffic).
-// Measured on B200: 6.3 TB/s, the same ceiling as st.global.v4 from all SMs (tools/fillbench.cu).
-constexpr int kFillDepth = 4;
-__global__ void __launch_bounds__(128) k_zero_fill_tma(unsigned char* __restrict__ out, long long num_chunks) {
+// ---- zero fill by TMA, short-lived CTAs ---------------------------------------------------------------
+// Each CTA zero-initialises one shared-memory tile (kFillBytes) and bulk-stores it ONCE
+// (cp.async.bulk.global.shared::cta -> UBLKCP), then exits.  Measured on B200 (tools/fillbench.cu, 2.67 GB):
+//   this form 7.5 TB/s  >  cudaMemsetAsync 7.3 TB/s  >  persistent TMA or st.global.v4 grid-stride loops 6.3 TB/s.
+__global__ void __launch_bounds__(128) k_zero_fill_tma(unsigned char* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char ztile[];
     for (int i = threadIdx.x; i < kFillBytes / 16; i += 128) reinterpret_cast<uint4*>(ztile)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     __syncthreads();
     if (threadIdx.x != 0) return;
-    int inflight = 0;
-    for (long long g = blockIdx.x; g < num_chunks; g += gridDim.x) {
-        bulk_store_s2g(out + g * kFillBytes, ztile, kFillBytes);
+    bulk_store_s2g(out + (size_t)blockIdx.x * kFillBytes, ztile, kFillBytes);
+    bulk_commit();
+    bulk_wait_read<0>();             // the tile must stay valid until the TMA engine has read it
+}
+
+// ---- ticketed single-launch fill + scatter --------------------------------------------------------------
+// One ordinary launch for the whole batch.  Every CTA draws a ticket (atomicAdd) that fixes its role:
+//   per sweep (frame-major):  kTicketFill fill CTAs (kTicketStores TMA bulk stores of a zero tile each, then
+//                             done[sweep] += 1 once the store has completed), followed by
+//                             chunks_per_sweep scatter CTAs (kBinChunk points each: transform, bin, RED.MAX).
+// A scatter CTA spins until done[sweep] == kTicketFill.  Tickets are handed out in start order, so every CTA a
+// scatter CTA waits for has already started and never waits itself: deadlock-free without a cooperative
+// launch.  The hardware's bounded CTA residency is the flow control: the fill front cannot run more than about
+// one sweep region ahead, so the atomics hit lines that are still dirty in L2 (61 G RED/s instead of 22).
+constexpr int kTicketRows = 5;
+constexpr int kTicketBytes = kTicketRows * kRowBytes;                // 14 400 B zero tile
+constexpr int kTicketStores = 4;                                     // bulk stores per fill CTA (57.6 KB contiguous)
+constexpr int kTicketFill = kZ * kH / (kTicketRows * kTicketStores); // 580 fill CTAs per (frame, sweep)
+constexpr int kTicketThreads = 128;
+constexpr int kTicketItems = 4;
+constexpr int kTicketChunk = kTicketThreads * kTicketItems;          // 512 points per scatter CTA
+
+template <int MODE>
+__global__ void __launch_bounds__(kTicketThreads, 8) k_fill_scatter_ticket(LidarIn in, uint32_t* __restrict__ out,
+                                                                        uint32_t* __restrict__ ticket,
+                                                                        uint32_t* __restrict__ done,
+                                                                        uint32_t* __restrict__ err_flag, int chunks_per_sweep) {
+    extern __shared__ __align__(128) unsigned char ztile[];
+    __shared__ uint32_t s_ticket;
+    __shared__ int s_ok;
+    __shared__ double sT[12];
+    __shared__ int sRect[kMaxRects * 4];
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_ticket = atomicAdd(ticket, 1u); s_ok = 1; }
+    for (int i = tid; i < kTicketBytes / 16; i += kTicketThreads) reinterpret_cast<uint4*>(ztile)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    __syncthreads();
+    const uint32_t per_sweep = (uint32_t)(kTicketFill + chunks_per_sweep);
+    const uint32_t bs = s_ticket / per_sweep, k = s_ticket - bs * per_sweep;
+
+    if (k < (uint32_t)kTicketFill) {
+        // ---------------- fill CTA ----------------
+        if (tid != 0) return;
+        unsigned char* dst = reinterpret_cast<unsigned char*>(out) + ((size_t)bs * kTicketFill + k) * (size_t)(kTicketBytes * kTicketStores);
+#pragma unroll
+        for (int q = 0; q < kTicketStores; ++q) bulk_store_s2g(dst + (size_t)q * kTicketBytes, ztile, kTicketBytes);
         bulk_commit();
-        if (++inflight == kFillDepth) { bulk_wait_read<kFillDepth - 1>(); --inflight; }
+        bulk_wait_all<0>();                                  // writes performed
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        atomicAdd(&done[bs], 1u);
+        return;
     }
-    bulk_wait_all<0>();
+    // ---------------- scatter CTA ----------------
+    const int c = (int)(k - kTicketFill);
+    const int b = (int)bs / in.S;
+    const int beg = in.sweep_off[bs], end = in.sweep_off[bs + 1];
+    const long long chunk0 = (long long)beg + (long long)c * kTicketChunk;
+    if (chunk0 >= end) return;
+    int nrect; bool flip;
+    load_frame_consts(in, (int)bs, b, MODE, sT, sRect, nrect, flip);
+    RawPoint<MODE> raw[kTicketItems];
+#pragma unroll
+    for (int it = 0; it < kTicketItems; ++it) {     // point loads in flight while we wait for the fill
+        const long long i = chunk0 + it * kTicketThreads + tid;
+        raw[it] = load_point<MODE>(in, i, i < end);
+    }
+    if (tid == 0) {
+        unsigned spins = 0;
+        while (ld_acquire_u32(&done[bs]) < (uint32_t)kTicketFill) {
+            __nanosleep(64);
+            if (++spins > kSpinLimit) { s_ok = 0; atomicExch(err_flag, 1u); break; }   // never hang the GPU
+        }
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    uint32_t* region = out + (size_t)bs * kZ * kPlane;
+#pragma unroll
+    for (int it = 0; it < kTicketItems; ++it) {
+        const long long i = chunk0 + it * kTicketThreads + tid;
+        int row; uint32_t cell, bits;
+        if (i < end && point_record<MODE>(raw[it], sT, flip, sRect, nrect, row, cell, bits)) {
+            const uint32_t zb = cell / kW, px = cell - zb * kW;
+            atomicMax(region + ((size_t)zb * kH + row) * kW + px, bits);
+        }
+    }
 }
 
 // ---- atomic scatter into the zero-filled grid (no binning) ----------------------------------------------
@@ -485,17 +588,10 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
             timing_end(st);
         } else {
             if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
-            static int fill_grid = 0;
-            if (fill_grid == 0) {
-                int dev = 0, sms = 0;
-                BEVGEN_CUDA(cudaGetDevice(&dev));
-                BEVGEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-                fill_grid = sms * 4;
-            }
             const long long nchunks = (long long)B * S * kFillPerSweep;
-            const int g = nchunks < fill_grid ? (int)nchunks : fill_grid;
+            if (nchunks > 0x7FFFFFFFll) return BEVGEN_E_UNSUPPORTED;
             BEVGEN_LAUNCH("k_zero_fill_tma", st,
-                          k_zero_fill_tma<<<g, 128, kFillBytes, st>>>(reinterpret_cast<unsigned char*>(out), nchunks));
+                          k_zero_fill_tma<<<(unsigned)nchunks, 128, kFillBytes, st>>>(reinterpret_cast<unsigned char*>(out)));
         }
         if (chunks > 0) {
             BEVGEN_LAUNCH("k_scatter_atomic", st,
@@ -503,14 +599,33 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
         }
         return 0;
     }
-    if (algo == 2 || algo == 3) {   // fused fill + scatter (3 = with warp-level dedupe)
-        const size_t need = ((size_t)B * S + 64) * sizeof(uint32_t);
+    if (algo == 5) {   // ticketed single-launch fill + scatter
+        const size_t nsw_sz = (size_t)B * S;
+        const size_t need = (nsw_sz + 64) * sizeof(uint32_t);
         if (!workspace || workspace_bytes < need) return BEVGEN_E_WORKSPACE;
         if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
         uint32_t* done = static_cast<uint32_t*>(workspace);
-        uint32_t* err_flag = done + (size_t)B * S;
+        uint32_t* ticket = done + nsw_sz;
+        uint32_t* err_flag = ticket + 1;
         BEVGEN_CUDA(cudaMemsetAsync(done, 0, need, st));
-        void (*kern)(LidarIn, uint32_t*, uint32_t*, uint32_t*, int, int) =
+        const int cps = max_sweep_points > 0 ? (max_sweep_points + kTicketChunk - 1) / kTicketChunk : 0;
+        const long long total = (long long)nsw_sz * (kTicketFill + cps);
+        if (total > 0x7FFFFFFFll) return BEVGEN_E_UNSUPPORTED;
+        BEVGEN_LAUNCH("k_fill_scatter_ticket", st,
+                      k_fill_scatter_ticket<MODE><<<(unsigned)total, kTicketThreads, kTicketBytes, st>>>(
+                          in, reinterpret_cast<uint32_t*>(out), ticket, done, err_flag, cps));
+        return 0;
+    }
+    if (algo == 2 || algo == 3) {   // fused fill + scatter (3 = with warp-level dedupe)
+        const size_t nsw_sz = (size_t)B * S;
+        const size_t need = (2 * nsw_sz + 64) * sizeof(uint32_t);
+        if (!workspace || workspace_bytes < need) return BEVGEN_E_WORKSPACE;
+        if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
+        uint32_t* done = static_cast<uint32_t*>(workspace);
+        uint32_t* scat = done + nsw_sz;
+        uint32_t* err_flag = scat + nsw_sz;
+        BEVGEN_CUDA(cudaMemsetAsync(done, 0, need, st));
+        void (*kern)(LidarIn, uint32_t*, uint32_t*, uint32_t*, uint32_t*, int, int) =
             algo == 3 ? k_fill_scatter<MODE, true> : k_fill_scatter<MODE, false>;
         static int grid_cached[4] = {0, 0, 0, 0};
         int& grid = grid_cached[(algo - 2) * 2 + MODE];
@@ -524,9 +639,9 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
             grid = sms * occ;
         }
         uint32_t* outu = reinterpret_cast<uint32_t*>(out);
-        int nsw = B * S, cps = chunks > 0 ? chunks : 1;
+        int nsw = B * S, cps = max_sweep_points > 0 ? (max_sweep_points + kScatChunk - 1) / kScatChunk : 1;
         LidarIn in_copy = in;
-        void* args[] = {&in_copy, &outu, &done, &err_flag, &nsw, &cps};
+        void* args[] = {&in_copy, &outu, &done, &scat, &err_flag, &nsw, &cps};
         timing_begin("k_fill_scatter", st);
         BEVGEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(kFusedThreads), args,
                                                 (size_t)kFillBytes, st));
