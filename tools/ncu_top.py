@@ -1,7 +1,8 @@
 """Print the top stall sites of a kernel from an .ncu-rep (source page, SASS view)."""
 import csv, subprocess, sys
 rep = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+kf = ["-k", "regex:" + sys.argv[3], "-c", "1"] if len(sys.argv) > 3 else []
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *kf], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 out = []
 hdr = None

@@ -32,7 +32,12 @@ from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LI
 #   MEMSET_ATOMIC  cudaMemsetAsync + the same scatter kernel (library fill, kept as a comparison point)
 #   TICKET         ONE ordinary launch: ticket-ordered CTAs, per sweep 2320 TMA zero-fill CTAs then the scatter CTAs
 #                  (atomics land on L2-resident lines)
-ALGO_TILED, ALGO_ATOMIC, ALGO_FUSED, ALGO_FUSED_DEDUPE, ALGO_MEMSET_ATOMIC, ALGO_TICKET = 0, 1, 2, 3, 4, 5
+#   TILE_RED       bin by (sweep,row); one short-lived CTA per tile: TMA zero fill of the tile, then the tile's own
+#                  records as L2-resident RED.MAX (TILE_RED_DEDUPE: + __match_any_sync warp aggregation)
+#   TILE_SMEM      bin by (sweep,row); one short-lived CTA per tile: shared-memory tile, warp-aggregated atomicMax,
+#                  29 TMA bulk stores (no global atomics)
+(ALGO_TILED, ALGO_ATOMIC, ALGO_FUSED, ALGO_FUSED_DEDUPE, ALGO_MEMSET_ATOMIC, ALGO_TICKET, ALGO_TILE_RED,
+ ALGO_TILE_RED_DEDUPE, ALGO_TILE_SMEM) = range(9)
 MAX_DROP_RECTS = 5
 
 

@@ -412,6 +412,90 @@ __global__ void __launch_bounds__(kFusedThreads) k_fill_scatter(LidarIn in, uint
     }
 }
 
+// ---- pass 3'': one short-lived CTA per tile, shared-memory-privatised tile + TMA bulk store ---------------------
+// The CTA zero-fills a [29 x 720] float tile in shared memory, applies the tile's records with warp-aggregated
+// (__match_any_sync + __reduce_max_sync) shared-memory atomicMax, and flushes the tile with 29 TMA bulk stores
+// (one 2 880 B channel row each).  No global atomics at all; every output byte is written exactly once.
+// Two CTAs are resident per SM (2 x 83.5 KB of shared memory), so one tile is being built while the other drains.
+constexpr int kTileSmemThreads = 256;
+__global__ void __launch_bounds__(kTileSmemThreads, 2) k_tile_smem_store(const uint2* __restrict__ sorted,
+                                                                         const uint32_t* __restrict__ starts,
+                                                                         const uint32_t* __restrict__ counts,
+                                                                         float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* const tile = reinterpret_cast<uint32_t*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int t = blockIdx.x;
+    const int bs = t / kH, row = t - bs * kH;
+    const uint32_t start = starts[t], cnt = counts[t];
+    uint2 first = make_uint2(0xFFFFFFFFu, 0u);
+    if ((uint32_t)tid < cnt) first = sorted[start + tid];     // in flight while the tile is being zeroed
+    for (int i = tid; i < kRowTileElems / 4; i += kTileSmemThreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < cnt; i0 += kTileSmemThreads) {
+        const uint32_t i = i0 + tid;
+        uint2 r = make_uint2(0xFFFFFFFFu, 0u);
+        if (i0 == 0) r = first; else if (i < cnt) r = sorted[start + i];
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, r.x);
+        const uint32_t m = __reduce_max_sync(peers, r.y);
+        if (r.x != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicMax(&tile[r.x], m);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid < kZ) {
+        float* dst = out + ((size_t)(bs * kZ + tid) * kH + row) * kW;
+        bulk_store_s2g(dst, tile + tid * kW, kRowBytes);
+        bulk_commit();
+        bulk_wait_read<0>();
+    }
+}
+
+// ---- pass 3': one short-lived CTA per tile: TMA zero fill of the tile, then its records as L2-resident REDs ---
+// Tile = (frame, sweep, row) = 29 channel rows of 2 880 B.  The CTA bulk-stores ONE shared zero row 29 times
+// (cp.async.bulk.global.shared::cta, one store per channel row), waits for the stores to complete, and then
+// applies the tile's own records (from the row-binned list) with RED.MAX.  The lines were written by this very
+// CTA microseconds earlier, so the atomics hit the L2 and never read HBM (no read-modify-write traffic).
+// No shared-memory tile -> ~16 CTAs per SM in flight, which is what the short-lived TMA fill needs to reach
+// ~7.5 TB/s (tools/fillbench.cu).
+constexpr int kTileThreads = 128;
+template <bool DEDUPE>
+__global__ void __launch_bounds__(kTileThreads) k_tile_fill_red(const uint2* __restrict__ sorted, const uint32_t* __restrict__ starts,
+                                                                const uint32_t* __restrict__ counts, uint32_t* __restrict__ out) {
+    __shared__ __align__(128) uint4 zrow[kRowBytes / 16];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int t = blockIdx.x;                                 // tile id = (frame*S + sweep)*400 + row
+    const int bs = t / kH, row = t - bs * kH;
+    for (int i = tid; i < kRowBytes / 16; i += kTileThreads) zrow[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    const uint32_t start = starts[t], cnt = counts[t];
+    uint2 first = make_uint2(0xFFFFFFFFu, 0u);
+    if ((uint32_t)tid < cnt) first = sorted[start + tid];     // record load in flight during the fill
+    __syncthreads();
+    uint32_t* tile0 = out + ((size_t)bs * kZ * kH + row) * kW;   // channel stride = kPlane
+    if (tid < kZ) {
+        bulk_store_s2g(tile0 + (size_t)tid * kPlane, zrow, kRowBytes);
+        bulk_commit();
+        bulk_wait_all<0>();                                   // zero rows have landed
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    if (cnt == 0) return;                                     // uniform
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < cnt; i0 += kTileThreads) {
+        const uint32_t i = i0 + tid;
+        uint2 r = make_uint2(0xFFFFFFFFu, 0u);
+        if (i0 == 0) r = first; else if (i < cnt) r = sorted[start + i];
+        const bool have = r.x != 0xFFFFFFFFu;
+        const uint32_t zb = r.x / kW, px = r.x - zb * kW;
+        if (DEDUPE) {                                         // warp-aggregated: one RED per distinct voxel per warp
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, r.x);
+            const uint32_t m = __reduce_max_sync(peers, r.y);
+            if (have && lane == __ffs(peers) - 1) atomicMax(tile0 + (size_t)zb * kPlane + px, m);
+        } else if (have) {
+            atomicMax(tile0 + (size_t)zb * kPlane + px, r.y);
+        }
+    }
+}
+
 // ---- zero fill by TMA, short-lived CTAs ---------------------------------------------------------------
 // Each CTA zero-initialises one shared-memory tile (kFillBytes) and bulk-stores it ONCE
 // (cp.async.bulk.global.shared::cta -> UBLKCP), then exits.  Measured on B200 (tools/fillbench.cu, 2.67 GB):
@@ -528,15 +612,22 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint
         const long long i = chunk0 + it * kBinThreads + threadIdx.x;
         raw[it] = load_point<MODE>(in, i, i < end);
     }
+    uint32_t* addr[kBinItems];
+    uint32_t val[kBinItems];
 #pragma unroll
     for (int it = 0; it < kBinItems; ++it) {
         const long long i = chunk0 + it * kBinThreads + threadIdx.x;
         int row; uint32_t cell, bits;
+        addr[it] = nullptr; val[it] = 0;
         if (i < end && point_record<MODE>(raw[it], sT, flip, sRect, nrect, row, cell, bits)) {
             const uint32_t zb = cell / kW, px = cell - zb * kW;
-            atomicMax(out + ((size_t)(bs * kZ + zb) * kH + row) * kW + px, bits);
+            addr[it] = out + ((size_t)(bs * kZ + zb) * kH + row) * kW + px;
+            val[it] = bits;
         }
     }
+#pragma unroll
+    for (int it = 0; it < kBinItems; ++it)
+        if (addr[it]) atomicMax(addr[it], val[it]);
 }
 
 template <typename T>
@@ -649,7 +740,7 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
         ++g_launch_count;
         return 0;
     }
-    if (algo != 0) return BEVGEN_E_INVALID_ARG;
+    if (algo != 0 && algo != 6 && algo != 7 && algo != 8) return BEVGEN_E_INVALID_ARG;
     if (!workspace || workspace_bytes < bevgen_lidar_workspace_bytes(total_points, B, S)) return BEVGEN_E_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;   // bulk store needs 16 B alignment
     const WorkspaceLayout L = layout(total_points, B, S);
@@ -668,6 +759,25 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
     if (chunks > 0) {
         BEVGEN_LAUNCH("k_bin_scatter", st,
                       k_bin_scatter<<<bin_grid, kBinThreads, 0, st>>>(in.sweep_off, S, w.tmp, w.starts, w.cursor, w.sorted));
+    }
+    if (algo == 8) {
+        if (bins > 0x7FFFFFFFull) return BEVGEN_E_UNSUPPORTED;
+        static bool attr8 = false;
+        if (!attr8) {
+            BEVGEN_CUDA(cudaFuncSetAttribute(k_tile_smem_store, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileBytes));
+            attr8 = true;
+        }
+        BEVGEN_LAUNCH("k_tile_smem_store", st, k_tile_smem_store<<<(unsigned)bins, kTileSmemThreads, kTileBytes, st>>>(
+                          w.sorted, w.starts, w.counts, out));
+        return 0;
+    }
+    if (algo == 6 || algo == 7) {
+        if (bins > 0x7FFFFFFFull) return BEVGEN_E_UNSUPPORTED;
+        if (algo == 7) BEVGEN_LAUNCH("k_tile_fill_red", st, k_tile_fill_red<true><<<(unsigned)bins, kTileThreads, 0, st>>>(
+                                         w.sorted, w.starts, w.counts, reinterpret_cast<uint32_t*>(out)));
+        else BEVGEN_LAUNCH("k_tile_fill_red", st, k_tile_fill_red<false><<<(unsigned)bins, kTileThreads, 0, st>>>(
+                               w.sorted, w.starts, w.counts, reinterpret_cast<uint32_t*>(out)));
+        return 0;
     }
     if (g_num_sms == 0) {
         int dev = 0;
