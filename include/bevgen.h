@@ -146,8 +146,10 @@ typedef struct bevgen_aug_params {
     int32_t rects[BEVGEN_MAX_DROP_RECTS * 4];   /* y0, x0, ph, pw */
 } bevgen_aug_params;
 
+/* params = device copy, params_host = the same B structs in host memory (the launcher groups frames by
+ * (rotate?, scale?) class from the host copy and launches one specialised kernel per class). */
 int bevgen_augment(const float *src, float *dst, int B, int C, const bevgen_aug_params *params,
-                   bevgen_stream_t stream);
+                   const bevgen_aug_params *params_host, bevgen_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -134,8 +134,9 @@ def augment_grid(src: torch.Tensor, params: Sequence[AugParams], out: Optional[t
         out = torch.empty_like(src)
     elif out.shape != src.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.data_ptr() == src.data_ptr():
         raise ValueError("out must be a distinct contiguous float32 tensor of the same shape")
-    dparams = _dev(pack_params(params), torch.uint8, src.device)
-    rc = _native.lib().bevgen_augment(_ptr(src), _ptr(out), B, Cc, _ptr(dparams), _stream_ptr())
+    hparams = pack_params(params)
+    dparams = _dev(hparams, torch.uint8, src.device)
+    rc = _native.lib().bevgen_augment(_ptr(src), _ptr(out), B, Cc, _ptr(dparams), C.c_void_p(hparams.ctypes.data), _stream_ptr())
     _native.check(rc, "bevgen_augment")
     return out
 

@@ -77,9 +77,17 @@ __device__ __forceinline__ void resize_tap(int d, int dsize, int ssize, int& s0,
     w1 = f;
 }
 
+struct FrameList {                               // frames of one class, passed by value
+    int n;
+    int idx[60];
+};
+
+// One thread per output pixel (x fastest), looping over the C channels of its frame.  ROT / SCL are uniform per
+// launch (the host groups frames by class), so the channel loop carries no dead code: 1, 4, 4 or 16 taps per value.
+template <bool ROT, bool SCL>
 __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict__ src, float* __restrict__ dst, int C,
-                                                         const bevgen_aug_params* __restrict__ params) {
-    const int x = blockIdx.x * kAugThreads + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+                                                         const bevgen_aug_params* __restrict__ params, FrameList fl) {
+    const int x = blockIdx.x * kAugThreads + threadIdx.x, y = blockIdx.y, b = fl.idx[blockIdx.z];
     __shared__ bevgen_aug_params P;
     {
         const int* g = reinterpret_cast<const int*>(params + b);
@@ -87,61 +95,97 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
         for (int i = threadIdx.x; i < (int)(sizeof(bevgen_aug_params) / 4); i += kAugThreads) s[i] = g[i];
     }
     __syncthreads();
-    const bool flip = P.do_flip != 0, rot = P.do_rotate != 0;
+    const bool flip = P.do_flip != 0;
     int nrect = P.n_rects;
     nrect = nrect > kMaxRects ? kMaxRects : (nrect < 0 ? 0 : nrect);
     const bool dropped = nrect && in_rects(P.rects, nrect, y, x);
 
     // ---- geometry: which R (or F) values does this output pixel need, with which weights -------------
-    int nq = 1;                                    // 1 source point, or 4 for a scaled pixel
-    int qy[4] = {y, y, y, y}, qx[4] = {x, x, x, x};
+    constexpr int NQ = SCL ? 4 : 1;
+    int qy[NQ], qx[NQ];
+    qy[0] = y; qx[0] = x;
     float wx0 = 1.f, wx1 = 0.f, wy0 = 1.f, wy1 = 0.f;
     bool outside = false;                          // scaled-down frame: zero padding around the resized image
-    if (P.do_scale) {
+    if (SCL) {
         const int nh = (int)__dmul_rn((double)kH, P.scale), nw = (int)__dmul_rn((double)kW, P.scale);   // utils.py:457
         const bool crop = P.scale > 1.0;                                                             // utils.py:464
         const int h0 = crop ? (nh - kH) / 2 : (kH - nh) / 2, w0 = crop ? (nw - kW) / 2 : (kW - nw) / 2;
         const int ry = crop ? y + h0 : y - h0, rx = crop ? x + w0 : x - w0;
+        int sx0 = 0, sx1 = 0, sy0 = 0, sy1 = 0;
         if (ry < 0 || ry >= nh || rx < 0 || rx >= nw) {
             outside = true;
         } else {
-            int sx0, sx1, sy0, sy1;
             resize_tap(rx, nw, kW, sx0, sx1, wx0, wx1);
             resize_tap(ry, nh, kH, sy0, sy1, wy0, wy1);
-            nq = 4;
-            qy[0] = sy0; qx[0] = sx0; qy[1] = sy0; qx[1] = sx1; qy[2] = sy1; qx[2] = sx0; qy[3] = sy1; qx[3] = sx1;
         }
+        qy[0] = sy0; qx[0] = sx0;
+        if (NQ == 4) { qy[1] = sy0; qx[1] = sx1; qy[2] = sy1; qx[2] = sx0; qy[3] = sy1; qx[3] = sx1; }
     }
-    RotTap tap[4];
-    int direct[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        direct[q] = qy[q] * kW + flip_x(qx[q], flip);
-        if (rot && q < nq) tap[q] = rot_taps(P.minv, qy[q], qx[q], flip);
-    }
-
-    // ---- channel loop ---------------------------------------------------------------------------------
     const size_t pix = (size_t)y * kW + x;
     const float* sp = src + (size_t)b * C * kPlane;
     float* dp = dst + (size_t)b * C * kPlane + pix;
     if (dropped || outside) {
-        for (int c = 0; c < C; ++c) dp[(size_t)c * kPlane] = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < C; ++c) __stcs(dp + (size_t)c * kPlane, 0.f);
         return;
     }
-#pragma unroll 2
-    for (int c = 0; c < C; ++c) {
-        const float* plane = sp + (size_t)c * kPlane;
-        float r[4];
+    RotTap tap[ROT ? NQ : 1];
+    int direct[NQ];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (q < nq) r[q] = rot ? rot_eval(plane, tap[q]) : __ldg(plane + direct[q]);
-        float v = r[0];
-        if (nq == 4) {     // horizontal pass then vertical pass, float32, no FMA (resize.cpp HResize/VResize)
-            const float top = __fadd_rn(__fmul_rn(r[0], wx0), __fmul_rn(r[1], wx1));
-            const float bot = __fadd_rn(__fmul_rn(r[2], wx0), __fmul_rn(r[3], wx1));
-            v = __fadd_rn(__fmul_rn(top, wy0), __fmul_rn(bot, wy1));
+    for (int q = 0; q < NQ; ++q) {
+        direct[q] = qy[q] * kW + flip_x(qx[q], flip);
+        if (ROT) tap[q] = rot_taps(P.minv, qy[q], qx[q], flip);
+    }
+
+    // ---- channel loop: U channels per iteration, all loads issued before the first use ------------------
+    constexpr int U = (ROT && SCL) ? 2 : 4;
+    auto value = [&](const float (&r)[NQ]) -> float {
+        if (!SCL) return r[0];
+        // horizontal pass then vertical pass, float32, no FMA (resize.cpp HResize / VResize)
+        const float top = __fadd_rn(__fmul_rn(r[0], wx0), __fmul_rn(r[NQ > 1 ? 1 : 0], wx1));
+        const float bot = __fadd_rn(__fmul_rn(r[NQ > 2 ? 2 : 0], wx0), __fmul_rn(r[NQ > 3 ? 3 : 0], wx1));
+        return __fadd_rn(__fmul_rn(top, wy0), __fmul_rn(bot, wy1));
+    };
+    int c = 0;
+    for (; c + U <= C; c += U) {
+        float v[U][NQ][ROT ? 4 : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float* plane = sp + (size_t)(c + u) * kPlane;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (ROT) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[u][q][k] = tap[q].off[k] >= 0 ? __ldg(plane + tap[q].off[k]) : 0.f;
+                } else {
+                    v[u][q][0] = __ldg(plane + direct[q]);
+                }
+            }
         }
-        dp[(size_t)c * kPlane] = v;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float r[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (ROT) {
+                    float acc = __fmul_rn(v[u][q][0], tap[q].w[0]);
+                    acc = __fadd_rn(acc, __fmul_rn(v[u][q][1], tap[q].w[1]));
+                    acc = __fadd_rn(acc, __fmul_rn(v[u][q][2], tap[q].w[2]));
+                    acc = __fadd_rn(acc, __fmul_rn(v[u][q][3], tap[q].w[3]));
+                    r[q] = acc;
+                } else {
+                    r[q] = v[u][q][0];
+                }
+            }
+            __stcs(dp + (size_t)(c + u) * kPlane, value(r));
+        }
+    }
+    for (; c < C; ++c) {
+        const float* plane = sp + (size_t)c * kPlane;
+        float r[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) r[q] = ROT ? rot_eval(plane, tap[q]) : __ldg(plane + direct[q]);
+        __stcs(dp + (size_t)c * kPlane, value(r));
     }
 }
 
@@ -151,11 +195,32 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
 using namespace bevgen;
 
 extern "C" int bevgen_augment(const float* src, float* dst, int B, int C, const bevgen_aug_params* params,
-                              bevgen_stream_t stream) {
-    if (B <= 0 || C <= 0 || !src || !dst || !params || src == dst) return BEVGEN_E_INVALID_ARG;
-    if (B > 65535) return BEVGEN_E_UNSUPPORTED;
-    const dim3 grid(kW / kAugThreads, kH, B);
+                              const bevgen_aug_params* params_host, bevgen_stream_t stream) {
+    if (B <= 0 || C <= 0 || !src || !dst || !params || !params_host || src == dst) return BEVGEN_E_INVALID_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    BEVGEN_LAUNCH("k_augment", st, k_augment<<<grid, kAugThreads, 0, st>>>(src, dst, C, params));
+    // group frames by class (rotate?, scale?) so each launch runs a specialised channel loop
+    for (int cls = 0; cls < 4; ++cls) {
+        const bool rot = cls & 1, scl = cls & 2;
+        FrameList fl;
+        fl.n = 0;
+        auto flush = [&]() -> int {
+            if (fl.n == 0) return 0;
+            const dim3 grid(kW / kAugThreads, kH, fl.n);
+            if (rot && scl)  BEVGEN_LAUNCH("k_augment", st, k_augment<true, true><<<grid, kAugThreads, 0, st>>>(src, dst, C, params, fl));
+            else if (rot)    BEVGEN_LAUNCH("k_augment", st, k_augment<true, false><<<grid, kAugThreads, 0, st>>>(src, dst, C, params, fl));
+            else if (scl)    BEVGEN_LAUNCH("k_augment", st, k_augment<false, true><<<grid, kAugThreads, 0, st>>>(src, dst, C, params, fl));
+            else             BEVGEN_LAUNCH("k_augment", st, k_augment<false, false><<<grid, kAugThreads, 0, st>>>(src, dst, C, params, fl));
+            fl.n = 0;
+            return 0;
+        };
+        for (int b = 0; b < B; ++b) {
+            if ((params_host[b].do_rotate != 0) == rot && (params_host[b].do_scale != 0) == scl) {
+                fl.idx[fl.n++] = b;
+                if (fl.n == 60) { const int rc = flush(); if (rc) return rc; }
+            }
+        }
+        const int rc = flush();
+        if (rc) return rc;
+    }
     return 0;
 }
