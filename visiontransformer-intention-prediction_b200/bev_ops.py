@@ -36,8 +36,10 @@ from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LI
 #                  records as L2-resident RED.MAX (TILE_RED_DEDUPE: + __match_any_sync warp aggregation)
 #   TILE_SMEM      bin by (sweep,row); one short-lived CTA per tile: shared-memory tile, warp-aggregated atomicMax,
 #                  29 TMA bulk stores (no global atomics)
+#   BINNED         ONE binning pass into fixed-capacity (zbin, 10-row band) tile bins; one short-lived CTA per 28.8 KB
+#                  tile: shared-memory tile, warp-aggregated atomicMax, ONE TMA bulk store; overflow -> global RED
 (ALGO_TILED, ALGO_ATOMIC, ALGO_FUSED, ALGO_FUSED_DEDUPE, ALGO_MEMSET_ATOMIC, ALGO_TICKET, ALGO_TILE_RED,
- ALGO_TILE_RED_DEDUPE, ALGO_TILE_SMEM) = range(9)
+ ALGO_TILE_RED_DEDUPE, ALGO_TILE_SMEM, ALGO_BINNED) = range(10)
 MAX_DROP_RECTS = 5
 
 

@@ -129,3 +129,33 @@ class BevGenerator:
             if mp is not None:
                 mp = _aug.augment_grid(mp, gp, out=out_map)
         return {"lidar_bev": lid, "map_bev": mp}
+
+
+class PrefetchingGenerator:
+    """Overlaps the host->device copy of batch i+1 (own copy stream) with the generation of batch i.
+
+        pf = PrefetchingGenerator(gen)
+        h = pf.submit(batch0)
+        for nxt in batches[1:] + [None]:
+            cur, h = h, (pf.submit(nxt) if nxt is not None else None)
+            out = pf.run(cur, aug=...)
+    """
+
+    def __init__(self, gen: BevGenerator) -> None:
+        self.gen = gen
+        self.copy_stream = torch.cuda.Stream(device=gen.device)
+
+    def submit(self, batch: FrameBatch):
+        with torch.cuda.stream(self.copy_stream):
+            dev = self.gen.upload(batch)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return batch, dev, ev
+
+    def run(self, handle, aug: Optional[Sequence[_aug.AugParams]] = None, **kw) -> dict:
+        batch, dev, ev = handle
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in dev.values():
+            t.record_stream(cur)          # allocated on the copy stream, consumed on the compute stream
+        return self.gen.generate(batch, aug, dev=dev, **kw)
