@@ -211,7 +211,7 @@ def run_ours(args) -> None:
 
     wl = WORKLOADS[args.workload]
     B = args.batch or wl["batch"]
-    algo = {"atomic": bg.ALGO_ATOMIC, "tiled": bg.ALGO_TILED, "fused": bg.ALGO_FUSED, "memset": bg.ALGO_MEMSET_ATOMIC, "ticket": bg.ALGO_TICKET, "tilered": bg.ALGO_TILE_RED, "tileredd": bg.ALGO_TILE_RED_DEDUPE, "tilesmem": bg.ALGO_TILE_SMEM, "binned": bg.ALGO_BINNED}[args.algo]
+    algo = {"atomic": bg.ALGO_ATOMIC, "tiled": bg.ALGO_TILED, "memset": bg.ALGO_MEMSET_ATOMIC}[args.algo]
     frames, md = make_frames(args.workload, B, args.points, rank)
     table = bg.MapTable([bg.maps.parse_map_dict(md)]) if wl["map"] else None
     batch = bg.FrameBatch.pack(frames, 10, map_ids=[0] * B if wl["map"] else None)
@@ -341,10 +341,9 @@ def run_ours(args) -> None:
 
     kernels = {n: {"ms_per_step": ms / K, "launches_per_step": c / K} for n, (c, ms) in ktimes.items()}
     own_bytes = {   # algorithmic bytes one launch of each kernel must move, per frame
-        "k_zero_fill_tma": LIDAR_FRAME_BYTES, "cudaMemsetAsync": LIDAR_FRAME_BYTES, "k_raster_store": LIDAR_FRAME_BYTES, "k_tile_fill_red": LIDAR_FRAME_BYTES + pts_frame * 4, "k_tile_smem_store": LIDAR_FRAME_BYTES + pts_frame * 4, "k_tile_store": LIDAR_FRAME_BYTES + pts_frame * 4, "k_bin_fixed": pts_frame * 20,
-        "k_fill_scatter": LIDAR_FRAME_BYTES + pts_frame * 16, "k_fill_scatter_ticket": LIDAR_FRAME_BYTES + pts_frame * 16, "k_scatter_atomic": pts_frame * 16,
-        "k_bin_count": pts_frame * 24, "k_bin_scatter": pts_frame * 12, "k_map_expand": MAP_FRAME_BYTES,
-        "k_augment": 2 * (LIDAR_FRAME_BYTES + (MAP_FRAME_BYTES if wl["map"] else 0)),
+        "k_zero_fill_tma": LIDAR_FRAME_BYTES, "cudaMemsetAsync": LIDAR_FRAME_BYTES, "k_scatter_atomic": pts_frame * 16,
+        "k_bin_fixed": pts_frame * 16, "k_tile_store": LIDAR_FRAME_BYTES, "k_overflow_red": 0,
+        "k_map_expand": MAP_FRAME_BYTES, "k_augment": 2 * (LIDAR_FRAME_BYTES + (MAP_FRAME_BYTES if wl["map"] else 0)),
     }
     peak = FALLBACK_HBM_GBS
     peak_src = "fallback"
@@ -412,7 +411,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", default="atomic", choices=["atomic", "tiled", "fused", "memset", "ticket", "tilered", "tileredd", "tilesmem", "binned"])
+    ap.add_argument("--algo", default="atomic", choices=["atomic", "tiled", "memset"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--points", type=int, default=100_000, help="points per sweep")
     ap.add_argument("--no-parity", action="store_true")

@@ -37,6 +37,10 @@ extern "C" {
 #define BEVGEN_MAX_DROP_RECTS 5      /* utils.py:485 num_patches_range = (1, 5) */
 #define BEVGEN_MAX_POLYLINE_VERTS 1024
 
+#define BEVGEN_ALGO_TILED 0
+#define BEVGEN_ALGO_ATOMIC 1
+#define BEVGEN_ALGO_MEMSET_ATOMIC 2
+
 #define BEVGEN_E_INVALID_ARG (-1)
 #define BEVGEN_E_WORKSPACE   (-2)
 #define BEVGEN_E_UNSUPPORTED (-3)
@@ -85,11 +89,11 @@ int bevgen_transform_points_f64(const double *pts, int64_t n, int64_t stride, co
  *               -- only meaningful when no rotate/scale follows for that frame
  *
  * max_sweep_points: max over sweeps of the row count (host knows it; sizes the grid).
- * algo: 0 = tiled   bin by (sweep,row) -> shared-memory tile + warp-aggregated atomicMax -> TMA bulk store
- *       1 = atomic  TMA zero-fill kernel + global atomicMax scatter kernel
- *       2 = fused   one persistent cooperative kernel: TMA zero fill + dependent atomic scatter (3 = + warp dedupe)
- *       4 = cudaMemsetAsync + the scatter kernel of algo 1 (library fill; comparison point)
- *       All produce identical bits; workspace is needed for 0, 2, 3.
+ * algo: BEVGEN_ALGO_TILED          one binning pass into per-tile record bins; per 28.8 KB tile one CTA builds the tile
+ *                                  in shared memory (warp-aggregated atomicMax) and writes it with ONE TMA bulk store
+ *       BEVGEN_ALGO_ATOMIC         TMA zero-fill kernel + global RED.MAX scatter kernel              [fastest, default]
+ *       BEVGEN_ALGO_MEMSET_ATOMIC  cudaMemsetAsync + the same scatter kernel (library fill; comparison point)
+ *       All produce identical bits; a workspace is needed for TILED only.
  * ------------------------------------------------------------------------------------- */
 size_t bevgen_lidar_workspace_bytes(int64_t total_points, int B, int S);
 

@@ -17,7 +17,7 @@ def bg():
     return bevgen_b200
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_lidar_golden(bg, algo):
     z = load("lidar_c2_small.npz")
     got = bg.lidar_bev_from_sweeps(z["points4"], z["sweep_offsets"], z["rel_tf"], 1, 10, algo=algo)[0].cpu().numpy()

@@ -43,7 +43,7 @@ def _batch(frames, S):
     return pts, off, tf.reshape(-1, 4, 4)
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_fused_single_frame_matches_oracle(bg, co, algo):
     f = bg.synthetic.frame_c2(0, n=20_000)
     want = co.lidar_bev_fused(f.points4, f.sweep_offsets, f.rel_tf, 10)
@@ -53,7 +53,7 @@ def test_fused_single_frame_matches_oracle(bg, co, algo):
     assert np.count_nonzero(got) > 50_000
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_fused_ragged_batch(bg, co, algo):
     S = 10
     frames = [bg.synthetic.frame_c2(1, n=5_000), bg.synthetic.frame_c1(0, n=7_001),
@@ -77,7 +77,7 @@ def test_contention_cluster(bg, co):
     """config-4 style: all points in a handful of voxels (warp-aggregated atomics path)."""
     f = bg.synthetic.frame_c4(3, n=60_000)
     want = co.lidar_bev_fused(f.points4, f.sweep_offsets, f.rel_tf, 10)
-    for algo in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for algo in (0, 1, 2):
         got = bg.lidar_bev_from_sweeps(f.points4, f.sweep_offsets, f.rel_tf, 1, 10, algo=algo)[0].cpu().numpy()
         assert np.array_equal(got, want)
     assert np.count_nonzero(want) < 60_000
@@ -100,7 +100,7 @@ def test_bin_edges_and_non_finite(bg, co):
     off = np.array([0, n], np.int32)
     tf = np.eye(4)[None]
     want = co.lidar_bev_fused(p, off, tf, 1)
-    for algo in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for algo in (0, 1, 2):
         got = bg.lidar_bev_from_sweeps(p, off, tf, 1, 1, algo=algo)[0].cpu().numpy()
         assert np.array_equal(got, want)
 
@@ -150,7 +150,7 @@ def test_flip_and_dropout_fusion(bg, co):
     rects[0, :2] = [[100, 300, 50, 50], [0, 0, 20, 33]]
     rects[1, :5] = [[380, 700, 50, 50], [150, 340, 25, 45], [10, 10, 20, 20], [200, 0, 50, 20], [399, 719, 20, 20]]
     want = _oracle_frames(co, frames, S)
-    for algo in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for algo in (0, 1, 2):
         got = bg.lidar_bev_from_sweeps(pts, off, tf, 3, S, flip=flip, drop_rects=rects, drop_counts=cnt, algo=algo).cpu().numpy()
         for b in range(3):
             w = co.flip_w(want[b]) if flip[b] else want[b].copy()
@@ -160,7 +160,7 @@ def test_flip_and_dropout_fusion(bg, co):
 
 def test_full_size_frame_and_properties(bg, co):
     """config-2 frame at full size (10 x 100k points): oracle equality, permutation invariance,
-    batch-vs-single equivalence, tiled == atomic."""
+    batch-vs-single equivalence, tiled == atomic == memset."""
     f = bg.synthetic.frame_c2(0)
     want = co.lidar_bev_fused(f.points4, f.sweep_offsets, f.rel_tf, 10)
     got = bg.lidar_bev_from_sweeps(f.points4, f.sweep_offsets, f.rel_tf, 1, 10)
@@ -175,11 +175,9 @@ def test_full_size_frame_and_properties(bg, co):
     assert torch.equal(got, got2)
     g = bg.synthetic.frame_c4(0)
     pts, off, tf = _batch([f, g], 10)
-    both = bg.lidar_bev_from_sweeps(pts, off, tf, 2, 10)
+    both = bg.lidar_bev_from_sweeps(pts, off, tf, 2, 10, algo=0)
     assert torch.equal(both[0], got[0])
-    for algo in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for algo in (1, 2):
         other = bg.lidar_bev_from_sweeps(pts, off, tf, 2, 10, algo=algo)
         assert torch.equal(both, other), algo
-        if algo in (2, 3, 5):   # bounded dependency spins must never have timed out
-            assert bg.fused_spin_timeout_flag(2, 10, algo=algo) == 0
     assert torch.equal(both[1].cpu(), torch.from_numpy(co.lidar_bev_fused(g.points4, g.sweep_offsets, g.rel_tf, 10)))

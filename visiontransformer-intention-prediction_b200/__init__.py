@@ -6,8 +6,8 @@ Import as ``bevgen_b200`` (alias module at the repo root).
 """
 from . import constants, maps, pose, synthetic          # noqa: F401  (pure host modules)
 from . import _native                                    # noqa: F401
-from .bev_ops import (ALGO_ATOMIC, ALGO_BINNED, ALGO_FUSED, ALGO_FUSED_DEDUPE, ALGO_MEMSET_ATOMIC, ALGO_TICKET, ALGO_TILE_RED, ALGO_TILE_RED_DEDUPE, ALGO_TILE_SMEM, ALGO_TILED, fused_spin_timeout_flag, create_intentnet_lidar_bev, lidar_bev_from_ego_points,   # noqa: F401
-                      lidar_bev_from_sweeps, transform_points)
+from .bev_ops import (ALGO_ATOMIC, ALGO_MEMSET_ATOMIC, ALGO_TILED, create_intentnet_lidar_bev,   # noqa: F401
+                      lidar_bev_from_ego_points, lidar_bev_from_sweeps, transform_points)
 
 from . import augment, map_ops                           # noqa: F401,E402
 from .augment import (AugParams, augment_bev, augment_grid, draw_aug_params, random_bev_dropout,   # noqa: F401,E402
@@ -19,5 +19,5 @@ from .map_ops import MapTable, rasterize_map_ego_centric, rasterize_maps, world_
 
 __all__ = ["augment", "map_ops", "AugParams", "augment_bev", "augment_grid", "draw_aug_params", "random_bev_dropout",
            "random_flip_bev", "random_rotate_bev", "random_scale_bev", "MapTable", "rasterize_map_ego_centric",
-           "rasterize_maps", "world_to_bev_pixel", "ALGO_MEMSET_ATOMIC", "ALGO_TICKET", "ALGO_TILE_RED", "ALGO_TILE_RED_DEDUPE", "ALGO_TILE_SMEM", "ALGO_BINNED", "pipeline", "BevGenerator", "FrameBatch", "PrefetchingGenerator", "ALGO_FUSED", "ALGO_FUSED_DEDUPE", "fused_spin_timeout_flag","constants", "maps", "pose", "synthetic", "transform_points", "create_intentnet_lidar_bev",
+           "rasterize_maps", "world_to_bev_pixel", "ALGO_MEMSET_ATOMIC",  "pipeline", "BevGenerator", "FrameBatch", "PrefetchingGenerator", "constants", "maps", "pose", "synthetic", "transform_points", "create_intentnet_lidar_bev",
            "lidar_bev_from_sweeps", "lidar_bev_from_ego_points", "ALGO_TILED", "ALGO_ATOMIC"]

@@ -25,21 +25,12 @@ import torch
 from . import _native
 from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LIDAR_SWEEPS)
 
-# LiDAR algorithms (all bit-identical; bench.py / DESIGN.md record the measured ranking):
-#   TILED          bin by (sweep,row) -> shared-memory tile, warp-aggregated atomicMax -> TMA bulk store of the tile
-#   ATOMIC         TMA zero-fill kernel + one global-atomicMax scatter kernel            (hand-written only)
-#   FUSED[_DEDUPE] one persistent cooperative kernel: TMA zero fill + dependent atomic scatter
-#   MEMSET_ATOMIC  cudaMemsetAsync + the same scatter kernel (library fill, kept as a comparison point)
-#   TICKET         ONE ordinary launch: ticket-ordered CTAs, per sweep 2320 TMA zero-fill CTAs then the scatter CTAs
-#                  (atomics land on L2-resident lines)
-#   TILE_RED       bin by (sweep,row); one short-lived CTA per tile: TMA zero fill of the tile, then the tile's own
-#                  records as L2-resident RED.MAX (TILE_RED_DEDUPE: + __match_any_sync warp aggregation)
-#   TILE_SMEM      bin by (sweep,row); one short-lived CTA per tile: shared-memory tile, warp-aggregated atomicMax,
-#                  29 TMA bulk stores (no global atomics)
-#   BINNED         ONE binning pass into fixed-capacity (zbin, 10-row band) tile bins; one short-lived CTA per 28.8 KB
-#                  tile: shared-memory tile, warp-aggregated atomicMax, ONE TMA bulk store; overflow -> global RED
-(ALGO_TILED, ALGO_ATOMIC, ALGO_FUSED, ALGO_FUSED_DEDUPE, ALGO_MEMSET_ATOMIC, ALGO_TICKET, ALGO_TILE_RED,
- ALGO_TILE_RED_DEDUPE, ALGO_TILE_SMEM, ALGO_BINNED) = range(10)
+# LiDAR algorithms (bit-identical; bench.py / DESIGN.md section 3.1 record the measured ranking):
+#   ATOMIC (default)  TMA zero-fill kernel + one global RED.MAX scatter kernel
+#   TILED             one binning pass into per-tile record bins -> per 28.8 KB tile: shared-memory tile,
+#                     __match_any_sync-aggregated atomicMax, ONE TMA bulk store (each output byte written once)
+#   MEMSET_ATOMIC     cudaMemsetAsync + the same scatter kernel (library fill, comparison point only)
+ALGO_TILED, ALGO_ATOMIC, ALGO_MEMSET_ATOMIC = 0, 1, 2
 MAX_DROP_RECTS = 5
 
 
@@ -98,7 +89,7 @@ def _aug_fusion_args(B, flip, drop_rects, drop_counts, device):
 # =========================================================================== batched fast path
 def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_sweeps: int = LIDAR_SWEEPS, *,
                           max_sweep_points: Optional[int] = None, flip=None, drop_rects=None, drop_counts=None,
-                          out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
+                          out: Optional[torch.Tensor] = None, algo: int = ALGO_ATOMIC) -> torch.Tensor:
     """Fused dataset.py:339-340 + utils.py:62-106 for ``num_frames`` frames.
 
     points4        float32 [N,4]  (x, y, z, intensity) in each sweep's own frame, sweeps concatenated
@@ -132,7 +123,7 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
     L = _native.lib()
     ws = None
     wbytes = 0
-    if algo not in (ALGO_ATOMIC, ALGO_MEMSET_ATOMIC):
+    if algo == ALGO_TILED:
         wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
         ws = workspace.get("lidar", wbytes, device)
     rc = L.bevgen_lidar_bev_fused(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
@@ -143,7 +134,7 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
 
 def lidar_bev_from_ego_points(points3, intensity, sweep_offsets, num_frames: int, num_sweeps: int = LIDAR_SWEEPS, *,
                               max_sweep_points: Optional[int] = None, flip=None, drop_rects=None, drop_counts=None,
-                              out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
+                              out: Optional[torch.Tensor] = None, algo: int = ALGO_ATOMIC) -> torch.Tensor:
     """utils.py:62-106 on float64 points that are already in the ego frame (batched)."""
     device = _require_cuda()
     B, S = int(num_frames), int(num_sweeps)
@@ -166,24 +157,13 @@ def lidar_bev_from_ego_points(points3, intensity, sweep_offsets, num_frames: int
         raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
     L = _native.lib()
     ws, wbytes = None, 0
-    if algo not in (ALGO_ATOMIC, ALGO_MEMSET_ATOMIC):
+    if algo == ALGO_TILED:
         wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
         ws = workspace.get("lidar", wbytes, device)
     rc = L.bevgen_lidar_bev_ego_f64(_ptr(pts), _ptr(inten), _ptr(off), B, S, n, int(max_sweep_points),
                                     _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
     _native.check(rc, "bevgen_lidar_bev_ego_f64")
     return out
-
-
-def fused_spin_timeout_flag(num_frames: int, num_sweeps: int = LIDAR_SWEEPS, algo: int = 2) -> int:
-    """Debug/test hook: 1 if a bounded dependency spin of the last ALGO_FUSED / ALGO_TICKET call on this device
-    timed out (the result would then be incomplete).  Synchronises the stream."""
-    device = _require_cuda()
-    ws = workspace.get("lidar", 0, device)
-    torch.cuda.current_stream().synchronize()
-    n = num_frames * num_sweeps
-    idx = n + 1 if algo == ALGO_TICKET else 2 * n          # workspace layouts of csrc/lidar.cu
-    return int(ws[: (idx + 1) * 4].view(torch.int32)[idx].item())
 
 
 # =========================================================================== reference signatures
@@ -246,7 +226,7 @@ def _pack_sweeps(points_list: Sequence, intensity_list: Sequence, num_expected_s
 
 
 def create_intentnet_lidar_bev(points_list, intensity_list, num_expected_sweeps: int = LIDAR_SWEEPS, *,
-                               as_tensor: bool = False, algo: int = ALGO_TILED):
+                               as_tensor: bool = False, algo: int = ALGO_ATOMIC):
     """Drop-in for utils.py:62-106.
 
     points_list[s]   (N_s, >=3) points already in the current ego frame (float64 on the Dataset
