@@ -411,7 +411,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", default="atomic", choices=["atomic", "tiled", "memset"])
+    ap.add_argument("--algo", default="tiled", choices=["atomic", "tiled", "memset"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--points", type=int, default=100_000, help="points per sweep")
     ap.add_argument("--no-parity", action="store_true")

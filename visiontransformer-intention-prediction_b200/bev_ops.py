@@ -26,9 +26,9 @@ from . import _native
 from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LIDAR_SWEEPS)
 
 # LiDAR algorithms (bit-identical; bench.py / DESIGN.md section 3.1 record the measured ranking):
-#   ATOMIC (default)  TMA zero-fill kernel + one global RED.MAX scatter kernel
-#   TILED             one binning pass into per-tile record bins -> per 28.8 KB tile: shared-memory tile,
+#   TILED (default)   one binning pass into per-tile record bins -> per 28.8 KB tile: shared-memory tile,
 #                     __match_any_sync-aggregated atomicMax, ONE TMA bulk store (each output byte written once)
+#   ATOMIC            TMA zero-fill kernel + one global RED.MAX scatter kernel (faster on dense / skewed scenes)
 #   MEMSET_ATOMIC     cudaMemsetAsync + the same scatter kernel (library fill, comparison point only)
 ALGO_TILED, ALGO_ATOMIC, ALGO_MEMSET_ATOMIC = 0, 1, 2
 MAX_DROP_RECTS = 5
@@ -89,7 +89,7 @@ def _aug_fusion_args(B, flip, drop_rects, drop_counts, device):
 # =========================================================================== batched fast path
 def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_sweeps: int = LIDAR_SWEEPS, *,
                           max_sweep_points: Optional[int] = None, flip=None, drop_rects=None, drop_counts=None,
-                          out: Optional[torch.Tensor] = None, algo: int = ALGO_ATOMIC) -> torch.Tensor:
+                          out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
     """Fused dataset.py:339-340 + utils.py:62-106 for ``num_frames`` frames.
 
     points4        float32 [N,4]  (x, y, z, intensity) in each sweep's own frame, sweeps concatenated
@@ -134,7 +134,7 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
 
 def lidar_bev_from_ego_points(points3, intensity, sweep_offsets, num_frames: int, num_sweeps: int = LIDAR_SWEEPS, *,
                               max_sweep_points: Optional[int] = None, flip=None, drop_rects=None, drop_counts=None,
-                              out: Optional[torch.Tensor] = None, algo: int = ALGO_ATOMIC) -> torch.Tensor:
+                              out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
     """utils.py:62-106 on float64 points that are already in the ego frame (batched)."""
     device = _require_cuda()
     B, S = int(num_frames), int(num_sweeps)
@@ -226,7 +226,7 @@ def _pack_sweeps(points_list: Sequence, intensity_list: Sequence, num_expected_s
 
 
 def create_intentnet_lidar_bev(points_list, intensity_list, num_expected_sweeps: int = LIDAR_SWEEPS, *,
-                               as_tensor: bool = False, algo: int = ALGO_ATOMIC):
+                               as_tensor: bool = False, algo: int = ALGO_TILED):
     """Drop-in for utils.py:62-106.
 
     points_list[s]   (N_s, >=3) points already in the current ego frame (float64 on the Dataset

@@ -69,7 +69,7 @@ class BevBatchLoader:
 
     def __init__(self, samples: Sequence, batch_size: int, map_table: Optional[map_ops.MapTable] = None,
                  map_id_of: Optional[Callable] = None, is_train: bool = False, num_sweeps: int = 10,
-                 algo: int = bev_ops.ALGO_ATOMIC, drop_last: bool = False) -> None:
+                 algo: int = bev_ops.ALGO_TILED, drop_last: bool = False) -> None:
         self.samples, self.bs, self.is_train, self.S = samples, int(batch_size), is_train, num_sweeps
         self.map_id_of = map_id_of or (lambda s: 0)
         self.gen = pipeline.BevGenerator(map_table, algo=algo)

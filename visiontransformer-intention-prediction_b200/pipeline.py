@@ -75,7 +75,7 @@ class FrameBatch:
 class BevGenerator:
     """Owns the device-side state (map table, workspaces) and turns FrameBatches into model inputs."""
 
-    def __init__(self, map_table: Optional[map_ops.MapTable] = None, algo: int = bev_ops.ALGO_ATOMIC,
+    def __init__(self, map_table: Optional[map_ops.MapTable] = None, algo: int = bev_ops.ALGO_TILED,
                  device: Optional[torch.device] = None) -> None:
         self.device = device or bev_ops._require_cuda()
         self.map_table = map_table
