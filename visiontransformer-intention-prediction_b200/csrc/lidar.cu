@@ -121,7 +121,7 @@ constexpr int kFillPerSweep = kZ * kH / kFillRows;                   // 1160 chu
 //                    costing counter atomics.  One pass over the points, no histogram scan, no intermediate copy.
 //   k_tile_store     one 128-thread CTA per tile: zero a 28.8 KB shared-memory tile, apply the bin's records with
 //                    warp-aggregated (__match_any_sync + __reduce_max_sync) shared atomicMax, ONE TMA bulk store.
-//                    The record loads do not depend on the count load (fixed bin address), 7 CTAs are resident per SM.
+//                    7 CTAs are resident per SM.
 //   k_overflow_red   the (rare) overflow records as global RED.MAX after the tiles have landed.
 // Every output byte is written exactly once by the TMA; no global read-modify-write except for overflow records.
 constexpr int kBinCap = 128;                                         // records per tile bin (avg 40 at 100k pts/sweep)
@@ -240,20 +240,22 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
 }
 
 __global__ void __launch_bounds__(128) k_tile_store(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
-                                                    float* __restrict__ out, size_t tile0) {
+                                                    float* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char ztile[];
     uint32_t* const tile = reinterpret_cast<uint32_t*>(ztile);
     const int tid = threadIdx.x, lane = tid & 31;
-    const size_t t = tile0 + blockIdx.x;
-    const uint2 rec = __ldcs(bins + t * kBinCap + tid);          // speculative: independent of the count load
+    const size_t t = blockIdx.x;
     uint32_t n = __ldcs(cnt + t);
     for (int i = tid; i < kFillBytes / 16; i += 128) reinterpret_cast<uint4*>(ztile)[i] = make_uint4(0, 0, 0, 0);
     n = n < (uint32_t)kBinCap ? n : (uint32_t)kBinCap;
+    // only the records that exist are read (measured: speculative reads of empty slots cost more HBM read traffic in
+    // the write stream than the dependent load costs in latency -- 7 resident CTAs per SM hide it)
+    const bool have = (uint32_t)tid < n;
+    uint2 rec = make_uint2(0xFFFFFFFFu, 0u);
+    if (have) rec = __ldcs(bins + t * kBinCap + tid);
     __syncthreads();
     if (n) {                                                    // uniform
-        const bool have = (uint32_t)tid < n;
-        const uint32_t key = have ? rec.x : 0xFFFFFFFFu;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, rec.x);      // dedupe equal cells inside the warp
         const uint32_t m = __reduce_max_sync(peers, rec.y);
         if (have && lane == __ffs(peers) - 1) atomicMax(&tile[rec.x], m);
     }
@@ -402,7 +404,7 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
             const dim3 agg_grid((max_sweep_points + kAggChunk - 1) / kAggChunk, B * S);
             BEVGEN_LAUNCH("k_bin_fixed", st, k_bin_fixed<MODE><<<agg_grid, kAggThreads, kAggSmem, st>>>(in, cnt, bins, ovf_cnt, ovf, 0));
         }
-        BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<(unsigned)ntiles, 128, kFillBytes, st>>>(cnt, bins, out, (size_t)0));
+        BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<(unsigned)ntiles, 128, kFillBytes, st>>>(cnt, bins, out));
         if (chunks > 0)
             BEVGEN_LAUNCH("k_overflow_red", st, k_overflow_red<<<296, 256, 0, st>>>(ovf_cnt, ovf, reinterpret_cast<uint32_t*>(out)));
         return 0;
