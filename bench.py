@@ -62,9 +62,9 @@ def make_frames(workload: str, batch: int, points: int, rank: int):
     return frames, md
 
 
-def frame_bytes(frame_points: int, with_map: bool, map_verts: int) -> int:
+def frame_bytes(frame_points: int, with_map: bool, map_verts: int, point_bytes: int = 16) -> int:
     """algorithmic bytes per frame."""
-    b = frame_points * 16 + 10 * 128 + LIDAR_FRAME_BYTES
+    b = frame_points * point_bytes + 10 * 128 + LIDAR_FRAME_BYTES
     if with_map:
         b += MAP_FRAME_BYTES + map_verts * 16
     return b
@@ -213,8 +213,11 @@ def run_ours(args) -> None:
     B = args.batch or wl["batch"]
     algo = {"atomic": bg.ALGO_ATOMIC, "tiled": bg.ALGO_TILED, "memset": bg.ALGO_MEMSET_ATOMIC}[args.algo]
     frames, md = make_frames(args.workload, B, args.points, rank)
+    if args.points_dtype == "f16":
+        frames = [bg.synthetic.quantize_f16(f) for f in frames]
     table = bg.MapTable([bg.maps.parse_map_dict(md)]) if wl["map"] else None
-    batch = bg.FrameBatch.pack(frames, 10, map_ids=[0] * B if wl["map"] else None)
+    batch = bg.FrameBatch.pack(frames, 10, map_ids=[0] * B if wl["map"] else None,
+                               points_dtype=np.float16 if args.points_dtype == "f16" else np.float32)
     gen = bg.BevGenerator(table, algo=algo, device=dev)
     aug = None
     if wl["aug"]:
@@ -337,7 +340,7 @@ def run_ours(args) -> None:
     value = frames_total / (total_ms_plain / 1e3)
     pts_frame = int(batch.num_points / B)
     verts = int(table.verts.shape[0]) if table is not None else 0
-    fbytes = frame_bytes(pts_frame, wl["map"], verts)
+    fbytes = frame_bytes(pts_frame, wl["map"], verts, 8 if args.points_dtype == "f16" else 16)
 
     kernels = {n: {"ms_per_step": ms / K, "launches_per_step": c / K} for n, (c, ms) in ktimes.items()}
     own_bytes = {   # algorithmic bytes one launch of each kernel must move, per frame
@@ -386,7 +389,7 @@ def run_ours(args) -> None:
         "metric": "bev_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": total_ms_plain / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "batch_per_gpu": B, "sweeps": S, "points_per_frame": pts_frame, "algo": args.algo,
+        "config": {"workload": wl["desc"], "batch_per_gpu": B, "sweeps": S, "points_per_frame": pts_frame, "algo": args.algo, "points_dtype": args.points_dtype,
                    "l2": f"per step inputs {batch.h2d_bytes/1e6:.0f} MB + outputs {B*LIDAR_FRAME_BYTES/1e9:.1f} GB >> 126 MB L2",
                    "parity": parity, "sharding": "frames independent per rank, no data-path collective"},
         "gpoints_per_s": value * pts_frame / 1e9,
@@ -414,6 +417,8 @@ def main() -> None:
     ap.add_argument("--algo", default="tiled", choices=["atomic", "tiled", "memset"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--points", type=int, default=100_000, help="points per sweep")
+    ap.add_argument("--points-dtype", default="f32", choices=["f32", "f16"],
+                    help="f16: coordinates rounded to fp16-representable values (AV2 storage precision) and packed at 8 B/point")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

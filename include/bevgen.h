@@ -103,6 +103,15 @@ int bevgen_lidar_bev_fused(const float *pts4, const int32_t *sweep_offsets, cons
                            float *out, void *workspace, size_t workspace_bytes, int algo,
                            bevgen_stream_t stream);
 
+/* same as bevgen_lidar_bev_fused with the points packed as 4 x fp16 (x, y, z, intensity), 8 B per point: the precision
+ * AV2 sweeps are stored in (dataset.py:311-321 reads float16 x,y,z and uint8 intensity); fp16 -> fp64 widening is exact,
+ * so the result equals the reference's on the same values while halving the host->device bytes. */
+int bevgen_lidar_bev_fused_f16(const void *pts_h4, const int32_t *sweep_offsets, const double *rel_tf,
+                               int B, int S, int64_t total_points, int max_sweep_points,
+                               const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,
+                               float *out, void *workspace, size_t workspace_bytes, int algo,
+                               bevgen_stream_t stream);
+
 int bevgen_lidar_bev_ego_f64(const double *pts3, const float *intensity, const int32_t *sweep_offsets,
                              int B, int S, int64_t total_points, int max_sweep_points,
                              const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,

@@ -181,3 +181,16 @@ def test_full_size_frame_and_properties(bg, co):
         other = bg.lidar_bev_from_sweeps(pts, off, tf, 2, 10, algo=algo)
         assert torch.equal(both, other), algo
     assert torch.equal(both[1].cpu(), torch.from_numpy(co.lidar_bev_fused(g.points4, g.sweep_offsets, g.rel_tf, 10)))
+
+
+def test_fp16_packed_points(bg, co):
+    """AV2-precision input (4 x fp16, 8 B/point): identical to the float32 path / oracle on the same values."""
+    frames = [bg.synthetic.quantize_f16(bg.synthetic.frame_c2(70 + i, n=4_000)) for i in range(2)]
+    want = _oracle_frames(co, frames, 10)
+    fb = bg.FrameBatch.pack(frames, 10, points_dtype=np.float16)
+    assert fb.points4.dtype == torch.float16 and fb.h2d_bytes < 0.6 * bg.FrameBatch.pack(frames, 10).h2d_bytes
+    for algo in (0, 1):
+        got = bg.BevGenerator(algo=algo).generate(fb, with_map=False)["lidar_bev"].cpu().numpy()
+        assert np.array_equal(got, want), algo
+    with pytest.raises(ValueError):
+        bg.FrameBatch.pack([bg.synthetic.frame_c2(3, n=100)], 10, points_dtype=np.float16)   # not fp16-representable

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "bevgen_transform_points_f64": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "bevgen_lidar_workspace_bytes": (_sz, [_i64, _i, _i]),
     "bevgen_lidar_bev_fused": (_i, [_p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),
+    "bevgen_lidar_bev_fused_f16": (_i, [_p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),
     "bevgen_lidar_bev_ego_f64": (_i, [_p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),
     "bevgen_map_workspace_bytes": (_sz, [_i]),
     "bevgen_map_raster": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),

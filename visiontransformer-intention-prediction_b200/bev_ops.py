@@ -92,7 +92,8 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
                           out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
     """Fused dataset.py:339-340 + utils.py:62-106 for ``num_frames`` frames.
 
-    points4        float32 [N,4]  (x, y, z, intensity) in each sweep's own frame, sweeps concatenated
+    points4        float32 (16 B/pt) or float16 (8 B/pt, AV2's stored precision) [N,4]  (x, y, z, intensity) in each
+                   sweep's own frame, sweeps concatenated
     sweep_offsets  int32 [B*S+1]  CSR offsets; an empty range = missing sweep (its 29 channels stay 0)
     rel_tf         float64 [B*S,4,4]  ego_SE3_world @ sweep_SE3 (pose.sweep_rel_transforms)
     returns        float32 CUDA tensor [B, S*29, 400, 720]
@@ -102,11 +103,13 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
     host_off = None
     if not isinstance(sweep_offsets, torch.Tensor):
         host_off = np.ascontiguousarray(sweep_offsets, dtype=np.int32)
-    pts = _dev(points4, torch.float32, device)
+    half = (isinstance(points4, torch.Tensor) and points4.dtype == torch.float16) or \
+           (isinstance(points4, np.ndarray) and points4.dtype == np.float16)
+    pts = _dev(points4, torch.float16 if half else torch.float32, device)
     off = _dev(sweep_offsets, torch.int32, device)
     tf = _dev(rel_tf, torch.float64, device).reshape(-1, 16)
     if pts.dim() != 2 or pts.shape[1] != 4:
-        raise ValueError("points4 must be [N,4] float32 (x,y,z,intensity)")
+        raise ValueError("points4 must be [N,4] float32 or float16 (x,y,z,intensity)")
     if off.numel() != B * S + 1 or tf.shape[0] != B * S:
         raise ValueError("sweep_offsets must have B*S+1 entries and rel_tf B*S matrices")
     n = int(pts.shape[0])
@@ -126,8 +129,9 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
     if algo == ALGO_TILED:
         wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
         ws = workspace.get("lidar", wbytes, device)
-    rc = L.bevgen_lidar_bev_fused(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
-                                  _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
+    fn = L.bevgen_lidar_bev_fused_f16 if half else L.bevgen_lidar_bev_fused
+    rc = fn(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
+            _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
     _native.check(rc, "bevgen_lidar_bev_fused")
     return out
 

@@ -15,6 +15,8 @@
 //   MEMSET_ATOMIC     cudaMemsetAsync + k_scatter_atomic (library fill; kept only as a comparison point)
 #include "bevgen_common.cuh"
 
+#include <cuda_fp16.h>
+
 
 
 namespace bevgen {
@@ -27,6 +29,7 @@ constexpr int kBinChunk = kBinThreads * kBinItems;     // points per CTA
 constexpr int kRowBytes = kW * 4;                      // 2 880 (multiple of 16: bulk-copy legal)
 
 struct LidarIn {
+    const uint2* pts_h4;       // MODE 2: 4 x fp16 (x, y, z, intensity) = 8 B / point (AV2's on-disk precision)
     const float4* pts4;        // MODE 0
     const double* rel_tf;      // MODE 0: [B*S,16]
     const double* pts3;        // MODE 1
@@ -43,6 +46,7 @@ struct LidarIn {
 template <int MODE> struct RawPoint;
 template <> struct RawPoint<0> { float4 p; };
 template <> struct RawPoint<1> { double x, y, z; float v; };
+template <> struct RawPoint<2> { uint2 h; };
 
 template <int MODE>
 __device__ __forceinline__ RawPoint<MODE> load_point(const LidarIn& in, long long i, bool in_range);
@@ -63,7 +67,14 @@ __device__ __forceinline__ RawPoint<1> load_point<1>(const LidarIn& in, long lon
     return r;
 }
 
-// One point -> (row, cell-in-row-tile, intensity bits) or invalid.  MODE 0 transforms first.
+template <>
+__device__ __forceinline__ RawPoint<2> load_point<2>(const LidarIn& in, long long i, bool in_range) {
+    RawPoint<2> r;
+    r.h = in_range ? __ldcs(in.pts_h4 + i) : make_uint2(0u, 0u);               // streaming 8 B load, fully coalesced
+    return r;
+}
+
+// One point -> (row, cell-in-row-tile, intensity bits) or invalid.  MODE 0 / 2 transform first.
 template <int MODE>
 __device__ __forceinline__ bool point_record(const RawPoint<MODE>& raw, const double* sT, bool flip,
                                              const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits);
@@ -85,6 +96,15 @@ __device__ __forceinline__ bool point_record<0>(const RawPoint<0>& raw, const do
     return true;
 }
 template <>
+__device__ __forceinline__ bool point_record<2>(const RawPoint<2>& raw, const double* sT, bool flip,
+                                                const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits) {
+    // fp16 -> fp32 is exact, so this equals the reference reading float16 columns and widening to float64
+    const __half2 xy = *reinterpret_cast<const __half2*>(&raw.h.x), zi = *reinterpret_cast<const __half2*>(&raw.h.y);
+    RawPoint<0> f;
+    f.p = make_float4(__low2float(xy), __high2float(xy), __low2float(zi), __high2float(zi));
+    return point_record<0>(f, sT, flip, sRect, nrect, row, cell, bits);
+}
+template <>
 __device__ __forceinline__ bool point_record<1>(const RawPoint<1>& raw, const double*, bool flip,
                                                 const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits) {
     if (!(raw.v > 0.0f)) return false;
@@ -100,7 +120,7 @@ __device__ __forceinline__ bool point_record<1>(const RawPoint<1>& raw, const do
 
 __device__ __forceinline__ void load_frame_consts(const LidarIn& in, int bs, int b, int mode, double* sT, int* sRect,
                                                   int& nrect, bool& flip) {
-    if (mode == 0 && threadIdx.x < 12) sT[threadIdx.x] = in.rel_tf[(size_t)bs * 16 + threadIdx.x];
+    if (mode != 1 && threadIdx.x < 12) sT[threadIdx.x] = in.rel_tf[(size_t)bs * 16 + threadIdx.x];
     nrect = in.nrects ? in.nrects[b] : 0;
     nrect = nrect > kMaxRects ? kMaxRects : nrect;
     if ((int)threadIdx.x < 4 * nrect) sRect[threadIdx.x] = in.rects[(size_t)b * kMaxRects * 4 + threadIdx.x];
@@ -393,7 +413,7 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
         uint2* bins = reinterpret_cast<uint2*>(wp + L.bins);
         OvfRec* ovf = reinterpret_cast<OvfRec*>(wp + L.ovf);
         BEVGEN_CUDA(cudaMemsetAsync(cnt, 0, (ntiles + 64) * 4, st));
-        static bool attr_set[2] = {false, false};
+        static bool attr_set[3] = {false, false, false};
         if (!attr_set[MODE]) {
             BEVGEN_CUDA(cudaFuncSetAttribute(k_bin_fixed<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAggSmem));
             attr_set[MODE] = true;
@@ -429,8 +449,19 @@ extern "C" int bevgen_lidar_bev_fused(const float* pts4, const int32_t* sweep_of
                                       size_t workspace_bytes, int algo, bevgen_stream_t stream) {
     if (total_points > 0 && (!pts4 || !rel_tf)) return BEVGEN_E_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(pts4) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
-    LidarIn in{reinterpret_cast<const float4*>(pts4), rel_tf, nullptr, nullptr, sweep_offsets, flip, drop_rects, drop_counts, S};
+    LidarIn in{nullptr, reinterpret_cast<const float4*>(pts4), rel_tf, nullptr, nullptr, sweep_offsets, flip, drop_rects, drop_counts, S};
     return launch_lidar<0>(in, B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bevgen_lidar_bev_fused_f16(const void* pts_h4, const int32_t* sweep_offsets, const double* rel_tf, int B, int S,
+                                          int64_t total_points, int max_sweep_points, const uint8_t* flip,
+                                          const int32_t* drop_rects, const int32_t* drop_counts, float* out, void* workspace,
+                                          size_t workspace_bytes, int algo, bevgen_stream_t stream) {
+    if (total_points > 0 && (!pts_h4 || !rel_tf)) return BEVGEN_E_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(pts_h4) & 7u) != 0) return BEVGEN_E_INVALID_ARG;
+    LidarIn in{static_cast<const uint2*>(pts_h4), nullptr, rel_tf, nullptr, nullptr, sweep_offsets, flip, drop_rects, drop_counts, S};
+    return launch_lidar<2>(in, B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo,
                            static_cast<cudaStream_t>(stream));
 }
 
@@ -439,7 +470,7 @@ extern "C" int bevgen_lidar_bev_ego_f64(const double* pts3, const float* intensi
                                         const int32_t* drop_rects, const int32_t* drop_counts, float* out, void* workspace,
                                         size_t workspace_bytes, int algo, bevgen_stream_t stream) {
     if (total_points > 0 && (!pts3 || !intensity)) return BEVGEN_E_INVALID_ARG;
-    LidarIn in{nullptr, nullptr, pts3, intensity, sweep_offsets, flip, drop_rects, drop_counts, S};
+    LidarIn in{nullptr, nullptr, nullptr, pts3, intensity, sweep_offsets, flip, drop_rects, drop_counts, S};
     return launch_lidar<1>(in, B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo,
                            static_cast<cudaStream_t>(stream));
 }

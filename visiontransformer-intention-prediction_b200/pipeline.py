@@ -29,7 +29,7 @@ def _pinned(arr: np.ndarray) -> torch.Tensor:
 @dataclasses.dataclass
 class FrameBatch:
     """Host-side (pinned) packed batch."""
-    points4: torch.Tensor        # float32 [N,4]
+    points4: torch.Tensor        # float32 or float16 [N,4]
     sweep_offsets: torch.Tensor  # int32 [B*S+1]
     rel_tf: torch.Tensor         # float64 [B*S,16]
     ego_T: torch.Tensor          # float64 [B,9]
@@ -44,10 +44,11 @@ class FrameBatch:
 
     @property
     def h2d_bytes(self) -> int:
-        return int(self.points4.numel() * 4 + self.sweep_offsets.numel() * 4 + self.rel_tf.numel() * 8 + self.ego_T.numel() * 8)
+        return int(self.points4.numel() * self.points4.element_size() + self.sweep_offsets.numel() * 4 + self.rel_tf.numel() * 8 + self.ego_T.numel() * 8)
 
     @staticmethod
-    def pack(frames: Sequence, num_sweeps: int = LIDAR_SWEEPS, map_ids: Optional[Sequence[int]] = None) -> "FrameBatch":
+    def pack(frames: Sequence, num_sweeps: int = LIDAR_SWEEPS, map_ids: Optional[Sequence[int]] = None,
+             points_dtype=np.float32) -> "FrameBatch":
         """frames: objects with points4 [n,4] f32, sweep_offsets [s+1], sweep_poses [s,7], current_pose [7]
         (e.g. synthetic.Frame).  Sweeps beyond ``num_sweeps`` are an error, as in the reference (utils.py:102)."""
         B, S = len(frames), int(num_sweeps)
@@ -66,7 +67,15 @@ class FrameBatch:
         off[1:] = np.cumsum(counts.reshape(-1))
         if off[-1] >= 2 ** 31:
             raise ValueError("more than 2^31 points in one batch")
-        pts = np.concatenate([np.asarray(f.points4, np.float32).reshape(-1, 4) for f in frames], 0) if B else np.zeros((0, 4), np.float32)
+        pts = np.concatenate([np.asarray(f.points4).reshape(-1, 4) for f in frames], 0) if B else np.zeros((0, 4), np.float32)
+        if points_dtype == np.float16:
+            # lossless only if the values are fp16-representable (AV2 sweeps are stored as fp16 x,y,z + u8 intensity)
+            half = pts.astype(np.float16)
+            if not np.array_equal(half.astype(np.float32), pts.astype(np.float32), equal_nan=True):
+                raise ValueError("points are not exactly representable in float16; pack them as float32")
+            pts = half
+        else:
+            pts = pts.astype(np.float32)
         ids = np.full(B, -1, np.int64) if map_ids is None else np.asarray(map_ids, np.int64)
         return FrameBatch(_pinned(pts), _pinned(off.astype(np.int32)), _pinned(rel.reshape(B * S, 16)),
                           _pinned(ego.reshape(B, 9)), ids, B, S, int(counts.max()) if B else 0)
