@@ -72,3 +72,32 @@ def test_install_rebinds_reference_style_module(bg):
     pts = ds.transform_points(f.sweep(0)[:, :3], f.rel_tf[0])
     bev = ds.create_intentnet_lidar_bev([pts], [f.sweep(0)[:, 3]])
     assert bev.shape == (290, 400, 720) and bev.any()
+
+
+def test_partitioned_augmentation_equals_in_order_path(bg):
+    """resampled frames first (no identity copies) == the in-order path, up to the returned permutation"""
+    md = bg.synthetic.synthetic_map(seed=3, rows=9, cols=9, n_cross=4)
+    table = bg.MapTable([bg.maps.parse_map_dict(md)])
+    frames = _samples(bg, md, 6)
+    aug = [bg.AugParams(flip=True), bg.AugParams(angle_deg=5.0), bg.AugParams(), bg.AugParams(scale=1.03, rects=[(10, 20, 30, 40)]),
+           bg.AugParams(rects=[(100, 200, 50, 50)]), bg.AugParams(flip=True, angle_deg=-7.0, scale=0.97)]
+    gen = bg.BevGenerator(table)
+    ref = gen.generate(bg.FrameBatch.pack(frames, 10, map_ids=[0] * 6), aug)
+    ref_l, ref_m = ref["lidar_bev"].clone(), ref["map_bev"].clone()
+    f2, a2, order = bg.partition_for_augmentation(frames, aug)
+    assert order == [1, 3, 5, 0, 2, 4]
+    got = gen.generate(bg.FrameBatch.pack(f2, 10, map_ids=[0] * 6), a2)
+    for k, i in enumerate(order):
+        assert torch.equal(got["lidar_bev"][k], ref_l[i]), (k, i)
+        assert torch.equal(got["map_bev"][k], ref_m[i]), (k, i)
+    # loader with keep_order=False keeps grids and GT aligned
+    random.seed(5)
+    a = list(bg.dataset_shim.BevBatchLoader(frames, 6, table, is_train=True, keep_order=True))[0]
+    random.seed(5)
+    b = list(bg.dataset_shim.BevBatchLoader(frames, 6, table, is_train=True, keep_order=False))[0]
+    used = set()
+    for k in range(6):
+        match = [i for i in range(6) if i not in used and torch.equal(b["lidar_bev"][k], a["lidar_bev"][i])
+                 and torch.equal(b["gt_list"][k]["boxes_xywha"], a["gt_list"][i]["boxes_xywha"])]
+        assert match, k
+        used.add(match[0])

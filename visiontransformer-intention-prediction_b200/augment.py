@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .bev_ops import _dev, _ptr, _require_cuda, _stream_ptr
+from .bev_ops import _dev, _ptr, _require_cuda, _stream_ptr, to_numpy_fresh
 from .constants import GRID_HEIGHT_PX, GRID_WIDTH_PX, INTENTIONS_MAP
 
 _CV_PI = 3.1415926535897932384626433832795
@@ -179,8 +179,8 @@ def apply_gt(p: AugParams, boxes: np.ndarray, intentions: np.ndarray):
 # ------------------------------------------------------------------------------- reference signatures (numpy)
 def _apply_np(lidar_bev: np.ndarray, map_bev: np.ndarray, p: AugParams):
     dev = _require_cuda()
-    lo = augment_grid(_dev(lidar_bev, torch.float32, dev)[None], [p])[0].cpu().numpy()
-    mo = augment_grid(_dev(map_bev, torch.float32, dev)[None], [p])[0].cpu().numpy()
+    lo = to_numpy_fresh(augment_grid(_dev(lidar_bev, torch.float32, dev)[None], [p])[0])
+    mo = to_numpy_fresh(augment_grid(_dev(map_bev, torch.float32, dev)[None], [p])[0])
     return lo, mo
 
 
@@ -248,6 +248,6 @@ def augment_bev(lidar_bev, map_bev, gt_dict):
     lo = augment_grid(ld[None], [p])[0]
     mo = augment_grid(md[None], [p])[0]
     if not on_device:
-        lo, mo = lo.cpu().numpy(), mo.cpu().numpy()
+        lo, mo = to_numpy_fresh(lo), to_numpy_fresh(mo)
     gt = {"boxes_xywha": torch.from_numpy(np.asarray(boxes)).float(), "intentions": torch.from_numpy(np.asarray(intents)).long()}
     return lo, mo, gt

@@ -20,7 +20,6 @@ constexpr double kZMin = -2.0;
 constexpr double kZMax = 3.8;
 constexpr double kZSpan = kZMax - kZMin;   // folded in IEEE double exactly like Python's 3.8-(-2.0)
 constexpr int kPlane = kH * kW;            // 288 000
-constexpr int kRowTileElems = kZ * kW;     // one (sweep,row) tile: 29 x 720 floats = 83 520 B
 constexpr int kMaxRects = BEVGEN_MAX_DROP_RECTS;
 
 extern long long g_launch_count;           // host-side counter (cabi.cu)
@@ -145,8 +144,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {   // <= N groups may still be READING their smem source
     asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
 }
-template <int N>
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
 // order this thread's generic-proxy smem writes before later async-proxy (TMA) reads
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -69,12 +69,13 @@ class BevBatchLoader:
 
     def __init__(self, samples: Sequence, batch_size: int, map_table: Optional[map_ops.MapTable] = None,
                  map_id_of: Optional[Callable] = None, is_train: bool = False, num_sweeps: int = 10,
-                 algo: int = bev_ops.ALGO_TILED, drop_last: bool = False) -> None:
+                 algo: int = bev_ops.ALGO_TILED, drop_last: bool = False, keep_order: bool = True) -> None:
         self.samples, self.bs, self.is_train, self.S = samples, int(batch_size), is_train, num_sweeps
         self.map_id_of = map_id_of or (lambda s: 0)
         self.gen = pipeline.BevGenerator(map_table, algo=algo)
         self.with_map = map_table is not None
         self.drop_last = drop_last
+        self.keep_order = keep_order     # False: within a batch, resampled frames come first (gt_list permuted alike)
 
     def __len__(self) -> int:
         n = len(self.samples)
@@ -85,12 +86,14 @@ class BevBatchLoader:
             chunk = [s for s in self.samples[i0:i0 + self.bs] if s is not None]
             if not chunk or (self.drop_last and len(chunk) < self.bs):
                 continue
-            ids = [self.map_id_of(s) for s in chunk] if self.with_map else None
-            fb = pipeline.FrameBatch.pack(chunk, self.S, map_ids=ids)
             aug = None
             gts = []
             if self.is_train:
                 aug = [_aug.draw_aug_params(random) for _ in chunk]
+                if not self.keep_order:      # frames that rotate / scale first: no identity copies (order is returned)
+                    chunk, aug, _ = pipeline.partition_for_augmentation(chunk, aug)
+            ids = [self.map_id_of(s) for s in chunk] if self.with_map else None
+            fb = pipeline.FrameBatch.pack(chunk, self.S, map_ids=ids)
             for k, s in enumerate(chunk):
                 gt = getattr(s, "gt", None) or {"boxes_xywha": np.zeros((0, 5), np.float32), "intentions": np.zeros((0,), np.int64)}
                 boxes = np.array(gt["boxes_xywha"], dtype=np.float32, copy=True)

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _native, maps, pose
-from .bev_ops import _aug_fusion_args, _dev, _ptr, _require_cuda, _stream_ptr, workspace
+from .bev_ops import _aug_fusion_args, _dev, _ptr, _require_cuda, _stream_ptr, to_numpy_fresh, workspace
 from .constants import GRID_HEIGHT_PX, GRID_WIDTH_PX, MAP_CHANNELS
 
 
@@ -125,7 +125,7 @@ def rasterize_map_ego_centric(map_json_path: str, current_ego_pose, *, as_tensor
         print(f"Warning: Invalid ego quaternion. Returning empty map for {map_json_path}")
         return empty()
     out = rasterize_maps(table, [0], T3[None])[0]
-    return out if as_tensor else out.cpu().numpy()
+    return out if as_tensor else to_numpy_fresh(out)
 
 
 def world_to_bev_pixel(points_world_xy: np.ndarray, ego_tf_matrix: np.ndarray) -> np.ndarray:

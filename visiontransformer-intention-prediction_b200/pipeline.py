@@ -81,6 +81,17 @@ class FrameBatch:
                           _pinned(ego.reshape(B, 9)), ids, B, S, int(counts.max()) if B else 0)
 
 
+def partition_for_augmentation(frames: Sequence, aug: Sequence[_aug.AugParams]):
+    """Stable partition of a batch into [frames that rotate / scale ..., frames that do not ...].
+
+    Returns (frames, aug, order) with ``order[k]`` = original index of the frame now at position k.  A batch packed
+    in this order lets ``BevGenerator.generate`` write the non-resampled frames straight into the output tensor
+    (flip / dropout fused into generation) and run the gather kernel only over the frames that need it -- no identity
+    copies.  Batch order carries no meaning for training; permute ``gt_list`` with ``order`` to keep items aligned."""
+    idx = [i for i, p in enumerate(aug) if p.needs_gather] + [i for i, p in enumerate(aug) if not p.needs_gather]
+    return [frames[i] for i in idx], [aug[i] for i in idx], idx
+
+
 class BevGenerator:
     """Owns the device-side state (map table, workspaces) and turns FrameBatches into model inputs."""
 
@@ -112,31 +123,57 @@ class BevGenerator:
         frame rotates or scales, the batch goes through the single fused gather kernel."""
         B, S = batch.num_frames, batch.num_sweeps
         dv = dev if dev is not None else self.upload(batch)
-        gather = aug is not None and any(p.needs_gather for p in aug)
         flip = rects = cnt = None
+        J = 0                                   # frames [0, J) go through the gather kernel
         if aug is not None:
             if len(aug) != B:
                 raise ValueError("one AugParams per frame")
             flip, rects, cnt = _aug.fusion_arrays(aug)
+            need = [p.needs_gather for p in aug]
+            J = sum(need)
+            if J and not all(need[:J]):
+                J = B                           # not partitioned (partition_for_augmentation): gather the whole batch
         lshape = (B, S * LIDAR_HEIGHT_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
         mshape = (B, MAP_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
-        gen_l = self._buf("gen_l", lshape) if gather else out_lidar
-        lid = bev_ops.lidar_bev_from_sweeps(dv["points4"], dv["sweep_offsets"], dv["rel_tf"], B, S,
-                                            max_sweep_points=batch.max_sweep_points, flip=flip, drop_rects=rects,
-                                            drop_counts=cnt, out=gen_l, algo=self.algo)
-        mp = None
-        if with_map:
-            if self.map_table is None or (batch.map_ids < 0).any():
-                raise ValueError("with_map=True needs a MapTable and a map id per frame")
-            gen_m = self._buf("gen_m", mshape) if gather else out_map
-            mp = map_ops.rasterize_maps(self.map_table, batch.map_ids, dv["ego_T"], flip=flip, drop_rects=rects,
-                                        drop_counts=cnt, out=gen_m)
-        if gather:
-            # flip / dropout of the frames that need no resampling were already fused above: identity for them here
-            gp = [p if p.needs_gather else _aug.AugParams() for p in aug]
-            lid = _aug.augment_grid(lid, gp, out=out_lidar)
-            if mp is not None:
-                mp = _aug.augment_grid(mp, gp, out=out_map)
+        if with_map and (self.map_table is None or (batch.map_ids < 0).any()):
+            raise ValueError("with_map=True needs a MapTable and a map id per frame")
+        if out_lidar is None:
+            out_lidar = torch.empty(lshape, dtype=torch.float32, device=self.device)
+        if with_map and out_map is None:
+            out_map = torch.empty(mshape, dtype=torch.float32, device=self.device)
+        d_flip = None if flip is None else bev_ops._dev(flip, torch.uint8, self.device)
+        d_rects = None if rects is None else bev_ops._dev(rects, torch.int32, self.device)
+        d_cnt = None if cnt is None else bev_ops._dev(cnt, torch.int32, self.device)
+        d_T = dv["ego_T"]
+        ids = batch.map_ids
+
+        def run(lo: int, hi: int, dst_l: torch.Tensor, dst_m: Optional[torch.Tensor]) -> None:
+            """generate frames [lo, hi) into dst_l / dst_m (sub-ranges are pointer offsets: CSR offsets are absolute)"""
+            sl = slice(lo, hi)
+            bev_ops.lidar_bev_from_sweeps(dv["points4"], dv["sweep_offsets"][lo * S:hi * S + 1], dv["rel_tf"][lo * S:hi * S],
+                                          hi - lo, S, max_sweep_points=batch.max_sweep_points,
+                                          flip=None if d_flip is None else d_flip[sl],
+                                          drop_rects=None if d_rects is None else d_rects[sl],
+                                          drop_counts=None if d_cnt is None else d_cnt[sl], out=dst_l, algo=self.algo)
+            if with_map:
+                map_ops.rasterize_maps(self.map_table, ids[sl], d_T[sl], flip=None if d_flip is None else d_flip[sl],
+                                       drop_rects=None if d_rects is None else d_rects[sl],
+                                       drop_counts=None if d_cnt is None else d_cnt[sl], out=dst_m)
+
+        if J == 0:
+            run(0, B, out_lidar, out_map)
+        else:
+            gen_l = self._buf("gen_l", (J,) + lshape[1:])
+            gen_m = self._buf("gen_m", (J,) + mshape[1:]) if with_map else None
+            run(0, J, gen_l, gen_m)
+            if J < B:
+                run(J, B, out_lidar[J:], out_map[J:] if with_map else None)
+            # flip / dropout of frames that need no resampling were fused above; identity for them if they are in [0, J)
+            gp = [p if p.needs_gather else _aug.AugParams() for p in aug[:J]]
+            _aug.augment_grid(gen_l, gp, out=out_lidar[:J])
+            if with_map:
+                _aug.augment_grid(gen_m, gp, out=out_map[:J])
+        lid, mp = out_lidar, (out_map if with_map else None)
         return {"lidar_bev": lid, "map_bev": mp}
 
 
