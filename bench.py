@@ -208,6 +208,7 @@ def run_ours(args) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _native.lib()
+    numa = bg.sharding.bind_to_gpu_numa_node(local) if world > 1 else "numa: single rank, not bound"
 
     wl = WORKLOADS[args.workload]
     B = args.batch or wl["batch"]
@@ -404,7 +405,7 @@ def run_ours(args) -> None:
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "batch_per_gpu": B, "sweeps": S, "points_per_frame": pts_frame, "algo": args.algo, "points_dtype": args.points_dtype,
                    "l2": f"per step inputs {batch.h2d_bytes/1e6:.0f} MB + outputs {B*LIDAR_FRAME_BYTES/1e9:.1f} GB >> 126 MB L2",
-                   "parity": parity, "sharding": "frames independent per rank, no data-path collective"},
+                   "parity": parity, "sharding": "frames independent per rank, no data-path collective", "host_affinity": numa},
         "gpoints_per_s": value * pts_frame / 1e9,
         "bytes_per_frame": fbytes, "step_algorithmic_gbs": step_gbs, "step_frac_of_peak": step_gbs / peak,
         "roofline": roofline, "kernels": kernels, "ms_per_step_with_event_timing": total_ms / K,

@@ -9,7 +9,7 @@ Two layers, both thin (PyTorch is used for device memory and streams only):
     ``rasterize_map_ego_centric``     utils.py:108-182      (map_ops.py)
     ``augment_bev`` / ``random_*``    utils.py:394-517      (augment.py)
 * the batched, device-resident fast path (``lidar_bev_from_sweeps`` ...) that replaces
-  transform + scatter for a whole batch of frames in four kernel launches and writes the
+  transform + scatter for a whole batch of frames in three kernel launches and writes the
   ``[B, 290, 400, 720]`` tensor the models consume (dataset.py:146-147, train_vit.py:154-159).
 
 No CPU fallback: every function here ends in a call into ``libbevgen_b200.so``.
