@@ -101,6 +101,9 @@ class BevGenerator:
         self.map_table = map_table
         self.algo = algo
         self._scratch = {}
+        # the map rasterizer is independent of the LiDAR kernels and far from saturating the GPU (one warp per lane
+        # segment): it runs on a side stream and is joined before the tensors are handed out
+        self._map_stream = torch.cuda.Stream(device=self.device)
 
     def _buf(self, key, shape) -> torch.Tensor:
         t = self._scratch.get(key)
@@ -156,10 +159,14 @@ class BevGenerator:
                                           drop_rects=None if d_rects is None else d_rects[sl],
                                           drop_counts=None if d_cnt is None else d_cnt[sl], out=dst_l, algo=self.algo)
             if with_map:
-                map_ops.rasterize_maps(self.map_table, ids[sl], d_T[sl], flip=None if d_flip is None else d_flip[sl],
-                                       drop_rects=None if d_rects is None else d_rects[sl],
-                                       drop_counts=None if d_cnt is None else d_cnt[sl], out=dst_m)
+                with torch.cuda.stream(self._map_stream):
+                    map_ops.rasterize_maps(self.map_table, ids[sl], d_T[sl], flip=None if d_flip is None else d_flip[sl],
+                                           drop_rects=None if d_rects is None else d_rects[sl],
+                                           drop_counts=None if d_cnt is None else d_cnt[sl], out=dst_m)
 
+        main = torch.cuda.current_stream()
+        if with_map:
+            self._map_stream.wait_stream(main)          # inputs (uploads, fusion arrays) are ready on the main stream
         if J == 0:
             run(0, B, out_lidar, out_map)
         else:
@@ -172,7 +179,10 @@ class BevGenerator:
             gp = [p if p.needs_gather else _aug.AugParams() for p in aug[:J]]
             _aug.augment_grid(gen_l, gp, out=out_lidar[:J])
             if with_map:
+                main.wait_stream(self._map_stream)
                 _aug.augment_grid(gen_m, gp, out=out_map[:J])
+        if with_map:
+            main.wait_stream(self._map_stream)
         lid, mp = out_lidar, (out_map if with_map else None)
         return {"lidar_bev": lid, "map_bev": mp}
 
