@@ -12,7 +12,7 @@ from .bev_ops import (ALGO_ATOMIC, ALGO_MEMSET_ATOMIC, ALGO_TILED, create_intent
 from . import augment, map_ops                           # noqa: F401,E402
 from .augment import (AugParams, augment_bev, augment_grid, draw_aug_params, random_bev_dropout,   # noqa: F401,E402
                       random_flip_bev, random_rotate_bev, random_scale_bev)
-from . import dataset_shim, sharding                     # noqa: F401,E402
+from . import dataset_shim, sharding, sweep_io                     # noqa: F401,E402
 from . import pipeline                                   # noqa: F401,E402
 from .pipeline import BevGenerator, FrameBatch, PrefetchingGenerator, partition_for_augmentation           # noqa: F401,E402
 from .map_ops import MapTable, rasterize_map_ego_centric, rasterize_maps, world_to_bev_pixel   # noqa: F401,E402

@@ -48,7 +48,7 @@ class FrameBatch:
 
     @staticmethod
     def pack(frames: Sequence, num_sweeps: int = LIDAR_SWEEPS, map_ids: Optional[Sequence[int]] = None,
-             points_dtype=np.float32) -> "FrameBatch":
+             points_dtype=None) -> "FrameBatch":
         """frames: objects with points4 [n,4] f32, sweep_offsets [s+1], sweep_poses [s,7], current_pose [7]
         (e.g. synthetic.Frame).  Sweeps beyond ``num_sweeps`` are an error, as in the reference (utils.py:102)."""
         B, S = len(frames), int(num_sweeps)
@@ -68,6 +68,8 @@ class FrameBatch:
         if off[-1] >= 2 ** 31:
             raise ValueError("more than 2^31 points in one batch")
         pts = np.concatenate([np.asarray(f.points4).reshape(-1, 4) for f in frames], 0) if B else np.zeros((0, 4), np.float32)
+        if points_dtype is None:             # auto: keep fp16 when every frame already is (sweep_io.load_frame)
+            points_dtype = np.float16 if (B and all(np.asarray(f.points4).dtype == np.float16 for f in frames)) else np.float32
         if points_dtype == np.float16:
             # lossless only if the values are fp16-representable (AV2 sweeps are stored as fp16 x,y,z + u8 intensity)
             half = pts.astype(np.float16)
