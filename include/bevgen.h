@@ -160,9 +160,12 @@ typedef struct bevgen_aug_params {
 } bevgen_aug_params;
 
 /* params = device copy, params_host = the same B structs in host memory (the launcher groups frames by
- * (rotate?, scale?) class from the host copy and launches one specialised kernel per class). */
+ * (rotate?, scale?) class from the host copy and launches one specialised kernel per class).
+ * workspace (optional, device): scratch of k * C*400*720*4 bytes, k >= 1; when present, frames that rotate AND scale
+ * run as two 4-tap passes through it (faster); without it they use the fused 16-tap gather.  Same bits either way. */
 int bevgen_augment(const float *src, float *dst, int B, int C, const bevgen_aug_params *params,
-                   const bevgen_aug_params *params_host, bevgen_stream_t stream);
+                   const bevgen_aug_params *params_host, void *workspace, size_t workspace_bytes,
+                   bevgen_stream_t stream);
 
 #ifdef __cplusplus
 }

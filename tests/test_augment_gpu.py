@@ -62,9 +62,10 @@ CASES = [
 def test_single_ops_and_compositions(bg, co, case):
     p = bg.AugParams(**CASES[case])
     g = _grid(["sparse", "dense", "binary"][case % 3], 3, case)
-    got = bg.augment_grid(torch.from_numpy(g).cuda()[None], [p])[0].cpu().numpy()
     want = _oracle_apply(co, g, p)
-    assert np.array_equal(got, want), (CASES[case], np.abs(got - want).max(), int((got != want).sum()))
+    for two_pass in (True, False):       # rotate+scale: two 4-tap passes through scratch vs the fused 16-tap gather
+        got = bg.augment_grid(torch.from_numpy(g).cuda()[None], [p], two_pass=two_pass)[0].cpu().numpy()
+        assert np.array_equal(got, want), (CASES[case], two_pass, np.abs(got - want).max(), int((got != want).sum()))
 
 
 def test_batch_with_mixed_params(bg, co):

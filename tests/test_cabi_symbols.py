@@ -56,7 +56,7 @@ def test_argument_validation_without_a_gpu():
     assert L.bevgen_world_to_bev_pixel(null, 0, T, null, null) == 0
     assert L.bevgen_world_to_bev_pixel(null, 3, T, null, null) == INVALID
     # augmentation: in-place is refused
-    assert L.bevgen_augment(one, one, 1, 3, one, one, null) == INVALID
-    assert L.bevgen_augment(one, C.c_void_p(32), 0, 3, one, one, null) == INVALID
+    assert L.bevgen_augment(one, one, 1, 3, one, one, null, 0, null) == INVALID
+    assert L.bevgen_augment(one, C.c_void_p(32), 0, 3, one, one, null, 0, null) == INVALID
     for code in (INVALID, WORKSPACE, -3):
         assert L.bevgen_error_string(code).decode().startswith("bevgen:")

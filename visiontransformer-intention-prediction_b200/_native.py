@@ -72,7 +72,7 @@ PROTOTYPES = {
     "bevgen_map_workspace_bytes": (_sz, [_i]),
     "bevgen_map_raster": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "bevgen_world_to_bev_pixel": (_i, [_p, _i64, _p, _p, _p]),
-    "bevgen_augment": (_i, [_p, _p, _i, _i, _p, _p, _p]),
+    "bevgen_augment": (_i, [_p, _p, _i, _i, _p, _p, _p, _sz, _p]),
 }
 
 

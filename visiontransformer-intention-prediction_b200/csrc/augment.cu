@@ -79,7 +79,8 @@ __device__ __forceinline__ void resize_tap(int d, int dsize, int ssize, int& s0,
 
 struct FrameList {                               // frames of one class, passed by value
     int n;
-    int idx[60];
+    int use_flip, use_rects;                     // 0 = ignore the frame's flip / dropout in this pass (two-pass rotate+scale)
+    short src[60], dst[60], par[60];             // frame slot read, frame slot written, index into params
 };
 
 // One thread per output pixel (x fastest), looping over the C channels of its frame.  ROT / SCL are uniform per
@@ -87,16 +88,17 @@ struct FrameList {                               // frames of one class, passed 
 template <bool ROT, bool SCL>
 __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict__ src, float* __restrict__ dst, int C,
                                                          const bevgen_aug_params* __restrict__ params, FrameList fl) {
-    const int x = blockIdx.x * kAugThreads + threadIdx.x, y = blockIdx.y, b = fl.idx[blockIdx.z];
+    const int x = blockIdx.x * kAugThreads + threadIdx.x, y = blockIdx.y;
+    const int bsrc = fl.src[blockIdx.z], bdst = fl.dst[blockIdx.z];
     __shared__ bevgen_aug_params P;
     {
-        const int* g = reinterpret_cast<const int*>(params + b);
+        const int* g = reinterpret_cast<const int*>(params + fl.par[blockIdx.z]);
         int* s = reinterpret_cast<int*>(&P);
         for (int i = threadIdx.x; i < (int)(sizeof(bevgen_aug_params) / 4); i += kAugThreads) s[i] = g[i];
     }
     __syncthreads();
-    const bool flip = P.do_flip != 0;
-    int nrect = P.n_rects;
+    const bool flip = P.do_flip != 0 && fl.use_flip;
+    int nrect = fl.use_rects ? P.n_rects : 0;
     nrect = nrect > kMaxRects ? kMaxRects : (nrect < 0 ? 0 : nrect);
     const bool dropped = nrect && in_rects(P.rects, nrect, y, x);
 
@@ -122,8 +124,8 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
         if (NQ == 4) { qy[1] = sy0; qx[1] = sx1; qy[2] = sy1; qx[2] = sx0; qy[3] = sy1; qx[3] = sx1; }
     }
     const size_t pix = (size_t)y * kW + x;
-    const float* sp = src + (size_t)b * C * kPlane;
-    float* dp = dst + (size_t)b * C * kPlane + pix;
+    const float* sp = src + (size_t)bsrc * C * kPlane;
+    float* dp = dst + (size_t)bdst * C * kPlane + pix;
     if (dropped || outside) {
 #pragma unroll 8
         for (int c = 0; c < C; ++c) __stcs(dp + (size_t)c * kPlane, 0.f);
@@ -195,28 +197,50 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
 using namespace bevgen;
 
 extern "C" int bevgen_augment(const float* src, float* dst, int B, int C, const bevgen_aug_params* params,
-                              const bevgen_aug_params* params_host, bevgen_stream_t stream) {
+                              const bevgen_aug_params* params_host, void* workspace, size_t workspace_bytes,
+                              bevgen_stream_t stream) {
     if (B <= 0 || C <= 0 || !src || !dst || !params || !params_host || src == dst) return BEVGEN_E_INVALID_ARG;
+    if (B > 32767) return BEVGEN_E_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // group frames by class (rotate?, scale?) so each launch runs a specialised channel loop
+    const size_t frame_bytes = (size_t)C * kPlane * sizeof(float);
+    // rotate+scale frames: two 4-tap passes through a scratch frame are faster than the fused 16-tap gather (which is
+    // L1-throughput bound); the fused kernel stays as the exact fallback when no scratch is supplied.
+    const int scratch_slots = workspace ? (int)(workspace_bytes / frame_bytes) : 0;
+    float* ws = static_cast<float*>(workspace);
+    auto launch = [&](int cls, const float* s, float* d, const FrameList& fl) -> int {
+        const dim3 grid(kW / kAugThreads, kH, fl.n);
+        switch (cls) {
+            case 3:  BEVGEN_LAUNCH("k_augment", st, k_augment<true, true><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
+            case 1:  BEVGEN_LAUNCH("k_augment", st, k_augment<true, false><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
+            case 2:  BEVGEN_LAUNCH("k_augment", st, k_augment<false, true><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
+            default: BEVGEN_LAUNCH("k_augment", st, k_augment<false, false><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
+        }
+        return 0;
+    };
+    // group frames by class (bit0 rotate, bit1 scale) so each launch runs a specialised channel loop
     for (int cls = 0; cls < 4; ++cls) {
-        const bool rot = cls & 1, scl = cls & 2;
+        const int chunk = (cls == 3 && scratch_slots > 0) ? (scratch_slots < 60 ? scratch_slots : 60) : 60;
         FrameList fl;
-        fl.n = 0;
+        fl.n = 0; fl.use_flip = 1; fl.use_rects = 1;
         auto flush = [&]() -> int {
             if (fl.n == 0) return 0;
-            const dim3 grid(kW / kAugThreads, kH, fl.n);
-            if (rot && scl)  BEVGEN_LAUNCH("k_augment", st, k_augment<true, true><<<grid, kAugThreads, 0, st>>>(src, dst, C, params, fl));
-            else if (rot)    BEVGEN_LAUNCH("k_augment", st, k_augment<true, false><<<grid, kAugThreads, 0, st>>>(src, dst, C, params, fl));
-            else if (scl)    BEVGEN_LAUNCH("k_augment", st, k_augment<false, true><<<grid, kAugThreads, 0, st>>>(src, dst, C, params, fl));
-            else             BEVGEN_LAUNCH("k_augment", st, k_augment<false, false><<<grid, kAugThreads, 0, st>>>(src, dst, C, params, fl));
+            int rc;
+            if (cls == 3 && scratch_slots > 0) {
+                FrameList p1 = fl, p2 = fl;
+                p1.use_rects = 0; p2.use_flip = 0;
+                for (int j = 0; j < fl.n; ++j) { p1.dst[j] = (short)j; p2.src[j] = (short)j; }
+                if ((rc = launch(1, src, ws, p1)) != 0) return rc;     // flip + rotate  -> scratch
+                rc = launch(2, ws, dst, p2);                            // scale + dropout -> dst
+            } else {
+                rc = launch(cls, src, dst, fl);
+            }
             fl.n = 0;
-            return 0;
+            return rc;
         };
         for (int b = 0; b < B; ++b) {
-            if ((params_host[b].do_rotate != 0) == rot && (params_host[b].do_scale != 0) == scl) {
-                fl.idx[fl.n++] = b;
-                if (fl.n == 60) { const int rc = flush(); if (rc) return rc; }
+            if (((params_host[b].do_rotate != 0) | ((params_host[b].do_scale != 0) << 1)) == cls) {
+                fl.src[fl.n] = fl.dst[fl.n] = fl.par[fl.n] = (short)b;
+                if (++fl.n == chunk) { const int rc = flush(); if (rc) return rc; }
             }
         }
         const int rc = flush();

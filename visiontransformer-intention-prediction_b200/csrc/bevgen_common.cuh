@@ -85,20 +85,23 @@ static __device__ __noinline__ int lidar_voxel_exact(double x, double y, double 
 // t is further than kEps = 1e-6 from an integer; the (rare) near-integer points take the literal path.
 // Same argument for 300 - x/0.2 and for (z + 2)/5.8d*29 vs (z + 2)*5  (29/5.8d = 5(1 + 3e-17)).
 __device__ __forceinline__ bool lidar_voxel(double x, double y, double z, int& py, int& px, int& zb) {
-    if (!(z >= kZMin && z < kZMax)) return false;                       // utils.py:86-87 (exact compares)
+    if (!(z >= kZMin && z < kZMax)) return false;                       // utils.py:86-87 (exact compares; rejects NaN z)
     const double tx = __fma_rn(y, 5.0, kOffX);
     const double ty = __fma_rn(x, -5.0, kOffY);
-    if (!(tx > -0.5 && tx < (double)kW + 0.5 && ty > -0.5 && ty < (double)kH + 0.5)) return false;   // NaN -> false
     const double tz = __dmul_rn(__dsub_rn(z, kZMin), 5.0);
-    const double fx = floor(tx), fy = floor(ty), fz = floor(tz);
+    // floor via saturating conversions; NaN converts to 0 but then fails the "safely inside a cell" test below
+    const int ix = __double2int_rd(tx), iy = __double2int_rd(ty), iz = __double2int_rd(tz);
     constexpr double kEps = 1e-6;
-    const double dx = __dsub_rn(tx, fx), dy = __dsub_rn(ty, fy), dz = __dsub_rn(tz, fz);
+    const double dx = __dsub_rn(tx, (double)ix), dy = __dsub_rn(ty, (double)iy), dz = __dsub_rn(tz, (double)iz);
+    // written positively so that NaN / saturated values fall through to the literal path
+    const bool safe = dx >= kEps && dx <= 1.0 - kEps && dy >= kEps && dy <= 1.0 - kEps && dz >= kEps && dz <= 1.0 - kEps;
     int packed;
-    if (dx < kEps || dx > 1.0 - kEps || dy < kEps || dy > 1.0 - kEps || dz < kEps || dz > 1.0 - kEps) {
-        packed = lidar_voxel_exact(x, y, z);
+    if (safe) {
+        packed = ((unsigned)ix < (unsigned)kW && (unsigned)iy < (unsigned)kH) ? ((min(iz, kZ - 1) << 20) | (iy << 10) | ix) : -1;
     } else {
-        const int b = min((int)fz, kZ - 1);
-        packed = (fx >= 0.0 && fx < (double)kW && fy >= 0.0 && fy < (double)kH) ? ((b << 20) | ((int)fy << 10) | (int)fx) : -1;
+        // near a cell boundary (or non-finite): quick reject far outside the grid, else evaluate literally
+        if (!(tx > -0.5 && tx < (double)kW + 0.5 && ty > -0.5 && ty < (double)kH + 0.5)) return false;
+        packed = lidar_voxel_exact(x, y, z);
     }
     if (packed < 0) return false;
     px = packed & 1023; py = (packed >> 10) & 1023; zb = packed >> 20;

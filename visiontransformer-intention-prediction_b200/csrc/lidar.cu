@@ -74,48 +74,46 @@ __device__ __forceinline__ RawPoint<2> load_point<2>(const LidarIn& in, long lon
     return r;
 }
 
-// One point -> (row, cell-in-row-tile, intensity bits) or invalid.  MODE 0 / 2 transform first.
-template <int MODE>
-__device__ __forceinline__ bool point_record(const RawPoint<MODE>& raw, const double* sT, bool flip,
-                                             const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits);
-template <>
-__device__ __forceinline__ bool point_record<0>(const RawPoint<0>& raw, const double* sT, bool flip,
-                                                const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits) {
+// One point -> voxel (row py, column px after the optional flip, height bin zb) + intensity bits, or invalid.
+// MODE 0 / 2 transform first.
+struct Voxel { int py, px, zb; uint32_t bits; };
+
+__device__ __forceinline__ bool finish_voxel(double x, double y, double z, float v, bool flip, const int* sRect, int nrect,
+                                             Voxel& o) {
     // max with the +0.0 initial grid: only strictly positive intensities can change a voxel
     // (documented domain: finite or +inf, >= 0; then float max == unsigned max on the bit pattern)
-    if (!(raw.p.w > 0.0f)) return false;
-    double x, y, z;
-    xform_point(sT, (double)raw.p.x, (double)raw.p.y, (double)raw.p.z, x, y, z);
-    int py, px, zb;
-    if (!lidar_voxel(x, y, z, py, px, zb)) return false;
-    if (flip) px = kW - 1 - px;                           // utils.py:399 fused
-    if (nrect && in_rects(sRect, nrect, py, px)) return false;   // utils.py:496 fused
-    row = py;
-    cell = (uint32_t)(zb * kW + px);
-    bits = __float_as_uint(raw.p.w);
+    if (!(v > 0.0f)) return false;
+    if (!lidar_voxel(x, y, z, o.py, o.px, o.zb)) return false;
+    if (flip) o.px = kW - 1 - o.px;                                // utils.py:399 fused
+    if (nrect && in_rects(sRect, nrect, o.py, o.px)) return false;  // utils.py:496 fused
+    o.bits = __float_as_uint(v);
     return true;
 }
+
+template <int MODE>
+__device__ __forceinline__ bool point_voxel(const RawPoint<MODE>& raw, const double* sT, bool flip, const int* sRect, int nrect,
+                                            Voxel& o);
 template <>
-__device__ __forceinline__ bool point_record<2>(const RawPoint<2>& raw, const double* sT, bool flip,
-                                                const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits) {
+__device__ __forceinline__ bool point_voxel<0>(const RawPoint<0>& raw, const double* sT, bool flip, const int* sRect, int nrect,
+                                               Voxel& o) {
+    if (!(raw.p.w > 0.0f)) return false;                          // skip the FP64 work for no-op points
+    double x, y, z;
+    xform_point(sT, (double)raw.p.x, (double)raw.p.y, (double)raw.p.z, x, y, z);
+    return finish_voxel(x, y, z, raw.p.w, flip, sRect, nrect, o);
+}
+template <>
+__device__ __forceinline__ bool point_voxel<2>(const RawPoint<2>& raw, const double* sT, bool flip, const int* sRect, int nrect,
+                                               Voxel& o) {
     // fp16 -> fp32 is exact, so this equals the reference reading float16 columns and widening to float64
     const __half2 xy = *reinterpret_cast<const __half2*>(&raw.h.x), zi = *reinterpret_cast<const __half2*>(&raw.h.y);
     RawPoint<0> f;
     f.p = make_float4(__low2float(xy), __high2float(xy), __low2float(zi), __high2float(zi));
-    return point_record<0>(f, sT, flip, sRect, nrect, row, cell, bits);
+    return point_voxel<0>(f, sT, flip, sRect, nrect, o);
 }
 template <>
-__device__ __forceinline__ bool point_record<1>(const RawPoint<1>& raw, const double*, bool flip,
-                                                const int* sRect, int nrect, int& row, uint32_t& cell, uint32_t& bits) {
-    if (!(raw.v > 0.0f)) return false;
-    int py, px, zb;
-    if (!lidar_voxel(raw.x, raw.y, raw.z, py, px, zb)) return false;
-    if (flip) px = kW - 1 - px;
-    if (nrect && in_rects(sRect, nrect, py, px)) return false;
-    row = py;
-    cell = (uint32_t)(zb * kW + px);
-    bits = __float_as_uint(raw.v);
-    return true;
+__device__ __forceinline__ bool point_voxel<1>(const RawPoint<1>& raw, const double*, bool flip, const int* sRect, int nrect,
+                                               Voxel& o) {
+    return finish_voxel(raw.x, raw.y, raw.z, raw.v, flip, sRect, nrect, o);
 }
 
 __device__ __forceinline__ void load_frame_consts(const LidarIn& in, int bs, int b, int mode, double* sT, int* sRect,
@@ -188,17 +186,18 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
         for (int u = 0; u < 4; ++u) {
             const int k = (g + u) * kAggThreads + tid;
             const long long i = chunk0 + k;
-            int row = 0; uint32_t cell = 0, bits = 0;
-            const bool ok = (i < end) && point_record<MODE>(raw[u], sT, flip, sRect, nrect, row, cell, bits);
+            Voxel v;
+            v.bits = 0;
+            const bool ok = (i < end) && point_voxel<MODE>(raw[u], sT, flip, sRect, nrect, v);
             uint32_t word = 0xFFFFFFFFu;
             if (ok) {
-                const uint32_t zb = cell / kW, px = cell - zb * kW;
-                const uint32_t band = (uint32_t)row / kFillRows;
-                const uint32_t bin = zb * (kH / kFillRows) + band;
-                const uint32_t tcell = ((uint32_t)row - band * kFillRows) * kW + px;
+                const uint32_t band = (uint32_t)v.py / kFillRows;
+                const uint32_t bin = (uint32_t)v.zb * (kH / kFillRows) + band;
+                const uint32_t tcell = ((uint32_t)v.py - band * kFillRows) * kW + (uint32_t)v.px;
                 word = (bin << 13) | tcell;
                 rank[k] = (uint16_t)atomicAdd(&hist[bin], 1u);
             }
+            const uint32_t bits = v.bits;
             recs[k] = make_uint2(word, bits);
         }
     }
@@ -334,12 +333,11 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint
 #pragma unroll
     for (int it = 0; it < kBinItems; ++it) {
         const long long i = chunk0 + it * kBinThreads + threadIdx.x;
-        int row; uint32_t cell, bits;
+        Voxel v;
         addr[it] = nullptr; val[it] = 0;
-        if (i < end && point_record<MODE>(raw[it], sT, flip, sRect, nrect, row, cell, bits)) {
-            const uint32_t zb = cell / kW, px = cell - zb * kW;
-            addr[it] = out + ((size_t)(bs * kZ + zb) * kH + row) * kW + px;
-            val[it] = bits;
+        if (i < end && point_voxel<MODE>(raw[it], sT, flip, sRect, nrect, v)) {
+            addr[it] = out + ((size_t)(bs * kZ + v.zb) * kH + v.py) * kW + v.px;
+            val[it] = v.bits;
         }
     }
 #pragma unroll
