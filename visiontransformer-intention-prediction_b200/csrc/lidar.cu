@@ -135,8 +135,8 @@ constexpr int kFillPerSweep = kZ * kH / kFillRows;                   // 1160 chu
 // one chunk of the fast TMA fill kernel.  1160 tiles per sweep.
 //   k_bin_fixed      per point: transform, bin, rank inside the CTA (shared atomics); per touched tile ONE global
 //                    atomicAdd claims the CTA's slots; slot < kBinCap -> bins[tile][slot] = record, else -> overflow
-//                    list (dense scenes).  A full bin is detected with a plain load first, so a hot voxel stops
-//                    costing counter atomics.  One pass over the points, no histogram scan, no intermediate copy.
+//                    list (dense scenes; one list-append atomic per CTA).  One pass over the points, no histogram
+//                    scan, no intermediate copy.
 //   k_tile_store     one 128-thread CTA per tile: zero a 28.8 KB shared-memory tile, apply the bin's records with
 //                    warp-aggregated (__match_any_sync + __reduce_max_sync) shared atomicMax, ONE TMA bulk store.
 //                    7 CTAs are resident per SM.
@@ -202,15 +202,20 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
         }
     }
     __syncthreads();
-    // phase 2: one global claim per touched tile
-    for (int bin = tid; bin < kTilesPerSweep; bin += kAggThreads) {
-        const uint32_t c = hist[bin];
-        if (c) {
-            uint32_t* ctr = cnt + (size_t)bs * kTilesPerSweep + bin;
-            uint32_t b0 = __ldcg(ctr);                               // bin already full? then do not touch the counter
-            if (b0 < (uint32_t)kBinCap) b0 = atomicAdd(ctr, c);
-            base[bin] = b0;
+    // phase 2: one global claim per touched tile (all of a thread's claims are in flight together)
+    {
+        constexpr int kPer = (kTilesPerSweep + kAggThreads - 1) / kAggThreads;       // 3
+        uint32_t c[kPer], b0[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int bin = tid + j * kAggThreads;
+            c[j] = bin < kTilesPerSweep ? hist[bin] : 0u;
+            b0[j] = 0u;
+            if (c[j]) b0[j] = atomicAdd(cnt + (size_t)bs * kTilesPerSweep + bin, c[j]);
         }
+#pragma unroll
+        for (int j = 0; j < kPer; ++j)
+            if (c[j]) base[tid + j * kAggThreads] = b0[j];
     }
     __syncthreads();
     // phase 3: records to their slots; spills are ranked inside the CTA first (one shared atomic per warp) ...
