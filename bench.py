@@ -375,19 +375,24 @@ def run_ours(args) -> None:
     if mine:
         dom = max(mine, key=lambda n: mine[n]["ms_per_step"])
         k = kernels[dom]
-        per_launch_ms = k["ms_per_step"] / max(k["launches_per_step"], 1e-9)
-        frames_per_launch = B / max(k["launches_per_step"], 1e-9) if dom != "k_augment" else B
-        bytes_launch = own_bytes.get(dom, fbytes) * frames_per_launch
-        achieved = bytes_launch / (per_launch_ms / 1e3) / 1e9
+        # algorithmic bytes the kernel must move per STEP (it may take several launches: sub-ranges, frame classes)
+        if dom == "k_augment":
+            n_gather = sum(1 for p in (aug or []) if p.needs_gather)
+            bytes_step = n_gather * own_bytes["k_augment"]
+        else:
+            bytes_step = own_bytes.get(dom, fbytes) * B
+        launches = max(k["launches_per_step"], 1e-9)
+        achieved = bytes_step / (k["ms_per_step"] / 1e3) / 1e9
         traffic = None
         tpath = ROOT / "profiles" / "traffic.json"
-        if tpath.exists():
+        if tpath.exists() and args.workload == "c2" and B == WORKLOADS["c2"]["batch"]:
             try:
                 traffic = json.loads(tpath.read_text()).get(dom)
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_launch, "ms_per_launch": per_launch_ms}
+                    "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_step / launches,
+                    "ms_per_launch": k["ms_per_step"] / launches}
     step_gbs = fbytes * B / (total_ms_plain / K / 1e3) / 1e9
 
     e2e_value = frames_total / (e2e_ms / 1e3)
