@@ -227,7 +227,7 @@ def run_ours(args) -> None:
         frames, aug, _ = bg.partition_for_augmentation(frames, aug)     # resampled frames first: no identity copies
     batch = bg.FrameBatch.pack(frames, 10, map_ids=[0] * B if wl["map"] else None,
                                points_dtype=np.float16 if args.points_dtype == "f16" else np.float32)
-    gen = bg.BevGenerator(table, algo=algo, device=dev)
+    gen = bg.BevGenerator(table, algo=algo, device=dev, fused_augment=not args.dense_augment)
     S = 10
     out_l = torch.empty((B, S * 29, 400, 720), dtype=torch.float32, device=dev)
     out_m = torch.empty((B, 9, 400, 720), dtype=torch.float32, device=dev) if wl["map"] else None
@@ -361,7 +361,12 @@ def run_ours(args) -> None:
         "k_zero_fill_tma": LIDAR_FRAME_BYTES, "cudaMemsetAsync": LIDAR_FRAME_BYTES, "k_scatter_atomic": pts_frame * 16,
         "k_bin_fixed": pts_frame * 16, "k_tile_store": LIDAR_FRAME_BYTES, "k_overflow_red": 0,
         "k_map_expand": MAP_FRAME_BYTES, "k_augment": 2 * (LIDAR_FRAME_BYTES + (MAP_FRAME_BYTES if wl["map"] else 0)),
+        "k_tile_aug": LIDAR_FRAME_BYTES,
     }
+    n_gather = sum(1 for p in (aug or []) if p.needs_gather)
+    fused_aug = bool(aug) and "k_tile_aug" in kernels
+    if fused_aug:       # the gather then only covers the map grids of the resampled frames
+        own_bytes["k_augment"] = 2 * MAP_FRAME_BYTES
     peak = FALLBACK_HBM_GBS
     peak_src = "fallback"
     mp_path = ROOT / "MEASURED_PEAKS.json"
@@ -376,9 +381,10 @@ def run_ours(args) -> None:
         dom = max(mine, key=lambda n: mine[n]["ms_per_step"])
         k = kernels[dom]
         # algorithmic bytes the kernel must move per STEP (it may take several launches: sub-ranges, frame classes)
-        if dom == "k_augment":
-            n_gather = sum(1 for p in (aug or []) if p.needs_gather)
-            bytes_step = n_gather * own_bytes["k_augment"]
+        if dom in ("k_augment", "k_tile_aug"):
+            bytes_step = n_gather * own_bytes[dom]
+        elif dom == "k_tile_store" and fused_aug:
+            bytes_step = (B - n_gather) * own_bytes[dom]
         else:
             bytes_step = own_bytes.get(dom, fbytes) * B
         launches = max(k["launches_per_step"], 1e-9)
@@ -439,6 +445,8 @@ def main() -> None:
     ap.add_argument("--points", type=int, default=100_000, help="points per sweep")
     ap.add_argument("--points-dtype", default="f32", choices=["f32", "f16"],
                     help="f16: coordinates rounded to fp16-representable values (AV2 storage precision) and packed at 8 B/point")
+    ap.add_argument("--dense-augment", action="store_true",
+                    help="config 5: take the dense route (generate -> gather) instead of the fused generation+augmentation kernel")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

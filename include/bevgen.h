@@ -167,6 +167,26 @@ int bevgen_augment(const float *src, float *dst, int B, int C, const bevgen_aug_
                    const bevgen_aug_params *params_host, void *workspace, size_t workspace_bytes,
                    bevgen_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Generation FUSED with augmentation: out[b] = augment_bev's image part (utils.py:508-511: flip -> rotate ->
+ * scale -> dropout) applied to create_intentnet_lidar_bev of frame b (utils.py:62-106, with the per-sweep transform
+ * of dataset.py:339-340 in front), for a whole batch, with every output byte written exactly once: the un-augmented
+ * 334 MB grid of a frame that rotates or scales is never materialised (the dense route -- bevgen_lidar_bev_fused into a
+ * scratch grid, then bevgen_augment -- moves 3x the bytes).  Same bits as that route.
+ *   pts / pts_f16   float32 [N,4] (pts_f16 = 0) or 4 x fp16 per point (pts_f16 = 1); sweep_offsets, rel_tf as above
+ *   params          device array of B bevgen_aug_params; params_host = the same structs in host memory
+ *   workspace       bevgen_lidar_workspace_bytes(total_points, B, S)
+ * Returns BEVGEN_E_UNSUPPORTED when a frame's parameters are outside what the fused kernel's shared-memory tiles
+ * cover (never for the reference's own draws: |angle| <= 15 deg, 0.95 <= scale <= 1.05); query first with
+ * bevgen_aug_fused_supported (1 = every frame supported) and take the dense route otherwise.
+ * ------------------------------------------------------------------------------------- */
+int bevgen_aug_fused_supported(const bevgen_aug_params *params_host, int B);
+
+int bevgen_lidar_bev_augmented(const void *pts, int pts_f16, const int32_t *sweep_offsets, const double *rel_tf,
+                               int B, int S, int64_t total_points, int max_sweep_points,
+                               const bevgen_aug_params *params, const bevgen_aug_params *params_host,
+                               float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,6 +149,50 @@ def augment_grid(src: torch.Tensor, params: Sequence[AugParams], out: Optional[t
     return out
 
 
+def fused_supported(params: Sequence[AugParams]) -> bool:
+    """True when every frame's parameters fit the fused generation+augmentation tile kernel (always true for the
+    reference's own draws: |angle| <= 15 deg, 0.95 <= scale <= 1.05)."""
+    hp = pack_params(params)
+    return bool(_native.lib().bevgen_aug_fused_supported(C.c_void_p(hp.ctypes.data), len(params)))
+
+
+def lidar_bev_augmented(points4: torch.Tensor, sweep_offsets: torch.Tensor, rel_tf: torch.Tensor, num_frames: int,
+                        num_sweeps: int, params: Sequence[AugParams], *, max_sweep_points: int,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """create_intentnet_lidar_bev (utils.py:62-106) + the image part of augment_bev (utils.py:508-511) for a batch, every
+    output byte written once: frames that rotate / scale are built directly in augmented form from the binned point
+    records (csrc/lidar_aug_tile.cuh) instead of generate -> read back -> resample -> write.  Device tensors in
+    (points4 float32 or float16 [N,4], sweep_offsets int32 [B*S+1], rel_tf float64 [B*S,16]); returns float32
+    [B, S*29, 400, 720].  Raises if a frame's parameters are unsupported (see ``fused_supported``)."""
+    device = _require_cuda()
+    B, S = int(num_frames), int(num_sweeps)
+    if len(params) != B:
+        raise ValueError("one AugParams per frame")
+    if points4.dim() != 2 or points4.shape[1] != 4 or points4.dtype not in (torch.float32, torch.float16) or not points4.is_cuda:
+        raise ValueError("points4 must be a CUDA tensor [N,4] float32 or float16")
+    pts = points4.contiguous()
+    off = _dev(sweep_offsets, torch.int32, device)
+    tf = _dev(rel_tf, torch.float64, device).reshape(-1, 16)
+    if off.numel() != B * S + 1 or tf.shape[0] != B * S:
+        raise ValueError("sweep_offsets must have B*S+1 entries and rel_tf B*S matrices")
+    shape = (B, S * 29, GRID_HEIGHT_PX, GRID_WIDTH_PX)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
+    hparams = pack_params(params)
+    dparams = _dev(hparams, torch.uint8, device)
+    L = _native.lib()
+    n = int(pts.shape[0])
+    wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
+    ws = workspace.get("lidar", wbytes, device)
+    rc = L.bevgen_lidar_bev_augmented(_ptr(pts), 1 if pts.dtype == torch.float16 else 0, _ptr(off), _ptr(tf), B, S, n,
+                                      int(max_sweep_points), _ptr(dparams), C.c_void_p(hparams.ctypes.data), _ptr(out),
+                                      _ptr(ws), wbytes, _stream_ptr())
+    _native.check(rc, "bevgen_lidar_bev_augmented")
+    return out
+
+
 # ------------------------------------------------------------------------------- GT (host, reference semantics)
 def _wrap(a: np.ndarray) -> np.ndarray:
     return np.arctan2(np.sin(a), np.cos(a))

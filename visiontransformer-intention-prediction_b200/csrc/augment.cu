@@ -15,7 +15,7 @@
 // image, 1 read + 1 write of the grids instead of 3 + 3.
 // Geometry (tap offsets, weights) depends only on (y,x), not on the channel: it is computed once per
 // thread and reused for all C channels of the frame.
-#include "bevgen_common.cuh"
+#include "aug_geom.cuh"
 
 namespace bevgen {
 namespace {
@@ -29,19 +29,13 @@ struct RotTap {                                  // 4 taps of cv2's remapBilinea
 
 __device__ __forceinline__ int flip_x(int x, bool flip) { return flip ? kW - 1 - x : x; }
 
-// cv2.warpAffine coordinate scheme (imgwarp.cpp WarpAffineInvoker, INTER_LINEAR): AB_BITS 10, INTER_BITS 5
+// cv2.warpAffine coordinate scheme (aug_geom.cuh)
 __device__ __forceinline__ RotTap rot_taps(const double* __restrict__ M, int y, int x, bool flip) {
-    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]), 1024.0)) + 16;
-    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[4], (double)y), M[5]), 1024.0)) + 16;
-    const int ad = __double2int_rn(__dmul_rn(__dmul_rn(M[0], (double)x), 1024.0));
-    const int bd = __double2int_rn(__dmul_rn(__dmul_rn(M[3], (double)x), 1024.0));
-    const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+    const int X = (rot_X0(M, y) + rot_adelta(M, x)) >> 5, Y = (rot_Y0(M, y) + rot_bdelta(M, x)) >> 5;
     int sx = X >> 5, sy = Y >> 5;
     sx = max(-32768, min(32767, sx)); sy = max(-32768, min(32767, sy));      // saturate_cast<short>
-    const float fx = __fmul_rn((float)(X & 31), 0.03125f), fy = __fmul_rn((float)(Y & 31), 0.03125f);
-    const float tx0 = __fsub_rn(1.f, fx), ty0 = __fsub_rn(1.f, fy);
     RotTap t;
-    t.w[0] = __fmul_rn(ty0, tx0); t.w[1] = __fmul_rn(ty0, fx); t.w[2] = __fmul_rn(fy, tx0); t.w[3] = __fmul_rn(fy, fx);
+    rot_weights(X, Y, t.w);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int xx = sx + (k & 1), yy = sy + (k >> 1);
@@ -55,26 +49,7 @@ __device__ __forceinline__ float rot_eval(const float* __restrict__ plane, const
     const float v1 = t.off[1] >= 0 ? __ldg(plane + t.off[1]) : 0.f;
     const float v2 = t.off[2] >= 0 ? __ldg(plane + t.off[2]) : 0.f;
     const float v3 = t.off[3] >= 0 ? __ldg(plane + t.off[3]) : 0.f;
-    float r = __fmul_rn(v0, t.w[0]);
-    r = __fadd_rn(r, __fmul_rn(v1, t.w[1]));
-    r = __fadd_rn(r, __fmul_rn(v2, t.w[2]));
-    r = __fadd_rn(r, __fmul_rn(v3, t.w[3]));
-    return r;
-}
-
-// cv2.resize INTER_LINEAR source taps for destination index d (resize.cpp): f = (float)((d+0.5)*scale-0.5)
-__device__ __forceinline__ void resize_tap(int d, int dsize, int ssize, int& s0, int& s1, float& w0, float& w1) {
-    const double inv_scale = __ddiv_rn((double)dsize, (double)ssize);
-    const double scale = __ddiv_rn(1.0, inv_scale);
-    float f = __double2float_rn(__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5));
-    int s = (int)floorf(f);
-    f = __fsub_rn(f, (float)s);
-    if (s < 0) { f = 0.f; s = 0; }
-    if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
-    s0 = s;
-    s1 = s + 1 < ssize ? s + 1 : ssize - 1;
-    w0 = __fsub_rn(1.f, f);
-    w1 = f;
+    return rot_sum(v0, v1, v2, v3, t.w);
 }
 
 struct FrameList {                               // frames of one class, passed by value
@@ -109,9 +84,9 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
     float wx0 = 1.f, wx1 = 0.f, wy0 = 1.f, wy1 = 0.f;
     bool outside = false;                          // scaled-down frame: zero padding around the resized image
     if (SCL) {
-        const int nh = (int)__dmul_rn((double)kH, P.scale), nw = (int)__dmul_rn((double)kW, P.scale);   // utils.py:457
-        const bool crop = P.scale > 1.0;                                                             // utils.py:464
-        const int h0 = crop ? (nh - kH) / 2 : (kH - nh) / 2, w0 = crop ? (nw - kW) / 2 : (kW - nw) / 2;
+        const ScalePlacement sp_ = scale_placement(P.scale);                                          // utils.py:457, :464-471
+        const int nh = sp_.nh, nw = sp_.nw, h0 = sp_.h0, w0 = sp_.w0;
+        const bool crop = sp_.crop;
         const int ry = crop ? y + h0 : y - h0, rx = crop ? x + w0 : x - w0;
         int sx0 = 0, sx1 = 0, sy0 = 0, sy1 = 0;
         if (ry < 0 || ry >= nh || rx < 0 || rx >= nw) {
@@ -143,10 +118,7 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
     constexpr int U = (ROT && SCL) ? 2 : 4;
     auto value = [&](const float (&r)[NQ]) -> float {
         if (!SCL) return r[0];
-        // horizontal pass then vertical pass, float32, no FMA (resize.cpp HResize / VResize)
-        const float top = __fadd_rn(__fmul_rn(r[0], wx0), __fmul_rn(r[NQ > 1 ? 1 : 0], wx1));
-        const float bot = __fadd_rn(__fmul_rn(r[NQ > 2 ? 2 : 0], wx0), __fmul_rn(r[NQ > 3 ? 3 : 0], wx1));
-        return __fadd_rn(__fmul_rn(top, wy0), __fmul_rn(bot, wy1));
+        return resize_sum(r[0], r[NQ > 1 ? 1 : 0], r[NQ > 2 ? 2 : 0], r[NQ > 3 ? 3 : 0], wx0, wx1, wy0, wy1);
     };
     int c = 0;
     for (; c + U <= C; c += U) {
@@ -170,11 +142,7 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 if (ROT) {
-                    float acc = __fmul_rn(v[u][q][0], tap[q].w[0]);
-                    acc = __fadd_rn(acc, __fmul_rn(v[u][q][1], tap[q].w[1]));
-                    acc = __fadd_rn(acc, __fmul_rn(v[u][q][2], tap[q].w[2]));
-                    acc = __fadd_rn(acc, __fmul_rn(v[u][q][3], tap[q].w[3]));
-                    r[q] = acc;
+                    r[q] = rot_sum(v[u][q][0], v[u][q][1], v[u][q][2], v[u][q][3], tap[q].w);
                 } else {
                     r[q] = v[u][q][0];
                 }

@@ -150,4 +150,12 @@ __device__ __forceinline__ void bulk_wait_read() {   // <= N groups may still be
 // order this thread's generic-proxy smem writes before later async-proxy (TMA) reads
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+
+// ---- PTX wrappers: per-thread async copy global -> shared (LDGSTS), 8 bytes ---------------------
+__device__ __forceinline__ void cp_async_8(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 }  // namespace bevgen

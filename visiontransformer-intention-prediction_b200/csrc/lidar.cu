@@ -13,7 +13,7 @@
 //                                       (__match_any_sync) atomicMax, ONE TMA bulk store -- each output byte written once
 //                     k_overflow_red    overflow records as global RED.MAX
 //   MEMSET_ATOMIC     cudaMemsetAsync + k_scatter_atomic (library fill; kept only as a comparison point)
-#include "bevgen_common.cuh"
+#include "aug_geom.cuh"
 
 #include <cuda_fp16.h>
 
@@ -39,6 +39,9 @@ struct LidarIn {
     const int32_t* rects;      // [B,5,4] or null
     const int32_t* nrects;     // [B] or null
     int S;
+    // alternative source of the per-frame fusions (bevgen_lidar_bev_augmented): flip always; dropout rectangles only for
+    // frames that are not resampled afterwards (the fused tile kernel applies them to its output instead)
+    const bevgen_aug_params* aug = nullptr;   // [B] or null
 };
 
 // Raw point as loaded from HBM.  Loads are issued for ALL of a thread's items before the first use, so
@@ -119,6 +122,14 @@ __device__ __forceinline__ bool point_voxel<1>(const RawPoint<1>& raw, const dou
 __device__ __forceinline__ void load_frame_consts(const LidarIn& in, int bs, int b, int mode, double* sT, int* sRect,
                                                   int& nrect, bool& flip) {
     if (mode != 1 && threadIdx.x < 12) sT[threadIdx.x] = in.rel_tf[(size_t)bs * 16 + threadIdx.x];
+    if (in.aug) {
+        const bevgen_aug_params* P = in.aug + b;
+        nrect = (P->do_rotate | P->do_scale) ? 0 : P->n_rects;
+        nrect = nrect > kMaxRects ? kMaxRects : (nrect < 0 ? 0 : nrect);
+        if ((int)threadIdx.x < 4 * nrect) sRect[threadIdx.x] = P->rects[threadIdx.x];
+        flip = P->do_flip != 0;
+        return;
+    }
     nrect = in.nrects ? in.nrects[b] : 0;
     nrect = nrect > kMaxRects ? kMaxRects : nrect;
     if ((int)threadIdx.x < 4 * nrect) sRect[threadIdx.x] = in.rects[(size_t)b * kMaxRects * 4 + threadIdx.x];
@@ -248,9 +259,10 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
     __syncthreads();
     // ... phase 4: ONE global list-append atomic per CTA, then the spilled records go out
     if (s_spill_n == 0) return;                                      // uniform
-    if (tid == 0) s_spill_base = atomicAdd(ovf_cnt, s_spill_n);
+    // per-sweep lists: sweep bs owns ovf[sweep_off[bs] - sweep_off[0] ...) (a point spills at most once), count in ovf_cnt[bs]
+    if (tid == 0) s_spill_base = atomicAdd(ovf_cnt + bs, s_spill_n);
     __syncthreads();
-    const uint32_t obase = s_spill_base;
+    const uint32_t obase = (uint32_t)(beg - in.sweep_off[0]) + s_spill_base;
 #pragma unroll 1
     for (int it = 0; it < kAggItems; ++it) {
         const int k = it * kAggThreads + tid;
@@ -264,11 +276,11 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
 }
 
 __global__ void __launch_bounds__(128) k_tile_store(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
-                                                    float* __restrict__ out) {
+                                                    float* __restrict__ out, uint32_t t0) {
     extern __shared__ __align__(128) unsigned char ztile[];
     uint32_t* const tile = reinterpret_cast<uint32_t*>(ztile);
     const int tid = threadIdx.x, lane = tid & 31;
-    const size_t t = blockIdx.x;
+    const size_t t = (size_t)t0 + blockIdx.x;
     uint32_t n = __ldcs(cnt + t);
     for (int i = tid; i < kFillBytes / 16; i += 128) reinterpret_cast<uint4*>(ztile)[i] = make_uint4(0, 0, 0, 0);
     n = n < (uint32_t)kBinCap ? n : (uint32_t)kBinCap;
@@ -291,14 +303,24 @@ __global__ void __launch_bounds__(128) k_tile_store(const uint32_t* __restrict__
     bulk_wait_read<0>();
 }
 
+// grid (kOvfCtas, B*S): sweep blockIdx.y's overflow list.  With `aug`, sweeps of frames that are resampled are skipped
+// (k_tile_aug consumes their overflow records itself).
+constexpr int kOvfCtas = 4;
 __global__ void __launch_bounds__(256) k_overflow_red(const uint32_t* __restrict__ ovf_cnt, const OvfRec* __restrict__ ovf,
-                                                      uint32_t* __restrict__ out) {
-    const uint32_t n = *ovf_cnt;
-    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const OvfRec r = ovf[i];
+                                                      const int32_t* __restrict__ sweep_off, uint32_t* __restrict__ out,
+                                                      const bevgen_aug_params* __restrict__ aug, int S) {
+    const int bs = blockIdx.y;
+    const uint32_t n = ovf_cnt[bs];
+    if (n == 0) return;
+    if (aug) { const bevgen_aug_params* P = aug + bs / S; if (P->do_rotate | P->do_scale) return; }
+    const OvfRec* list = ovf + (sweep_off[bs] - sweep_off[0]);
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += kOvfCtas * 256) {
+        const OvfRec r = list[i];
         atomicMax(out + r.idx, r.bits);
     }
 }
+
+#include "lidar_aug_tile.cuh"
 
 // ---- zero fill by TMA, short-lived CTAs ---------------------------------------------------------------
 // Each CTA zero-initialises one shared-memory tile (kFillBytes) and bulk-stores it ONCE
@@ -371,7 +393,7 @@ TiledWorkspace tiled_layout(long long total_points, int B, int S) {
     TiledWorkspace w;
     const size_t ntiles = (size_t)B * S * kTilesPerSweep;
     size_t off = 0;
-    w.cnt = off;  off += align_up((ntiles + 64) * 4, 256);
+    w.cnt = off;  off += align_up((ntiles + (size_t)B * S + 64) * 4, 256);      // per-tile counts, then per-sweep overflow counts
     w.bins = off; off += align_up(ntiles * kBinCap * sizeof(uint2), 256);
     w.ovf = off;  off += align_up((size_t)total_points * sizeof(OvfRec), 256);
     w.bytes = off;
@@ -415,7 +437,7 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
         uint32_t* ovf_cnt = cnt + ntiles;
         uint2* bins = reinterpret_cast<uint2*>(wp + L.bins);
         OvfRec* ovf = reinterpret_cast<OvfRec*>(wp + L.ovf);
-        BEVGEN_CUDA(cudaMemsetAsync(cnt, 0, (ntiles + 64) * 4, st));
+        BEVGEN_CUDA(cudaMemsetAsync(cnt, 0, (ntiles + (size_t)B * S + 64) * 4, st));
         static bool attr_set[3] = {false, false, false};
         if (!attr_set[MODE]) {
             BEVGEN_CUDA(cudaFuncSetAttribute(k_bin_fixed<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAggSmem));
@@ -427,12 +449,93 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
             const dim3 agg_grid((max_sweep_points + kAggChunk - 1) / kAggChunk, B * S);
             BEVGEN_LAUNCH("k_bin_fixed", st, k_bin_fixed<MODE><<<agg_grid, kAggThreads, kAggSmem, st>>>(in, cnt, bins, ovf_cnt, ovf, 0));
         }
-        BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<(unsigned)ntiles, 128, kFillBytes, st>>>(cnt, bins, out));
+        BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<(unsigned)ntiles, 128, kFillBytes, st>>>(cnt, bins, out, 0u));
         if (chunks > 0)
-            BEVGEN_LAUNCH("k_overflow_red", st, k_overflow_red<<<296, 256, 0, st>>>(ovf_cnt, ovf, reinterpret_cast<uint32_t*>(out)));
+            BEVGEN_LAUNCH("k_overflow_red", st, k_overflow_red<<<dim3(kOvfCtas, B * S), 256, 0, st>>>(
+                              ovf_cnt, ovf, in.sweep_off, reinterpret_cast<uint32_t*>(out), nullptr, S));
         return 0;
     }
     return BEVGEN_E_INVALID_ARG;
+}
+
+// Generation + augmentation of a whole batch, every output byte written once (bevgen_lidar_bev_augmented):
+//   k_bin_fixed over all frames (flip fused for every frame; dropout rectangles fused for the frames that are not resampled)
+//   k_tile_store + k_overflow_red for the runs of frames that neither rotate nor scale
+//   k_tile_aug<ROT,SCL> per class for the others
+template <int MODE>
+int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int max_sweep_points,
+                           const bevgen_aug_params* params_host, float* out, void* workspace, size_t workspace_bytes,
+                           cudaStream_t st) {
+    if (B <= 0 || S <= 0 || total_points < 0 || max_sweep_points < 0 || !out || !in.sweep_off || !in.aug || !params_host)
+        return BEVGEN_E_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
+    const size_t ntiles = (size_t)B * S * kTilesPerSweep;
+    if (ntiles > 0x7FFFFFFFull || (unsigned)(B * S) > 65535u || B > 32767) return BEVGEN_E_UNSUPPORTED;
+    for (int b = 0; b < B; ++b)
+        if (!aug_tile_supported(params_host[b])) return BEVGEN_E_UNSUPPORTED;
+    const TiledWorkspace L = tiled_layout(total_points, B, S);
+    if (!workspace || workspace_bytes < L.bytes) return BEVGEN_E_WORKSPACE;
+    char* wp = static_cast<char*>(workspace);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(wp + L.cnt);
+    uint32_t* ovf_cnt = cnt + ntiles;
+    uint2* bins = reinterpret_cast<uint2*>(wp + L.bins);
+    OvfRec* ovf = reinterpret_cast<OvfRec*>(wp + L.ovf);
+    BEVGEN_CUDA(cudaMemsetAsync(cnt, 0, (ntiles + (size_t)B * S + 64) * 4, st));
+    static bool attr_set[3] = {false, false, false};
+    if (!attr_set[MODE]) {
+        BEVGEN_CUDA(cudaFuncSetAttribute(k_bin_fixed<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAggSmem));
+        attr_set[MODE] = true;
+    }
+    static bool aug_attr_set = false;
+    if (!aug_attr_set) {
+        BEVGEN_CUDA(cudaFuncSetAttribute(k_tile_aug<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AugTileCfg<true, false>::kSmem));
+        BEVGEN_CUDA(cudaFuncSetAttribute(k_tile_aug<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AugTileCfg<false, true>::kSmem));
+        BEVGEN_CUDA(cudaFuncSetAttribute(k_tile_aug<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AugTileCfg<true, true>::kSmem));
+        aug_attr_set = true;
+    }
+    const bool have_points = max_sweep_points > 0;
+    if (have_points) {
+        const dim3 agg_grid((max_sweep_points + kAggChunk - 1) / kAggChunk, B * S);
+        BEVGEN_LAUNCH("k_bin_fixed", st, k_bin_fixed<MODE><<<agg_grid, kAggThreads, kAggSmem, st>>>(in, cnt, bins, ovf_cnt, ovf, 0));
+    }
+    auto cls_of = [&](int b) { return (params_host[b].do_rotate != 0 ? 1 : 0) | (params_host[b].do_scale != 0 ? 2 : 0); };
+    // runs of frames that are not resampled: plain tile stores
+    bool any_plain = false;
+    for (int b = 0; b < B;) {
+        if (cls_of(b) != 0) { ++b; continue; }
+        int e = b;
+        while (e < B && cls_of(e) == 0) ++e;
+        const unsigned t0 = (unsigned)((size_t)b * S * kTilesPerSweep), nt = (unsigned)((size_t)(e - b) * S * kTilesPerSweep);
+        BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<nt, 128, kFillBytes, st>>>(cnt, bins, out, t0));
+        any_plain = true;
+        b = e;
+    }
+    if (any_plain && have_points)
+        BEVGEN_LAUNCH("k_overflow_red", st, k_overflow_red<<<dim3(kOvfCtas, B * S), 256, 0, st>>>(
+                          ovf_cnt, ovf, in.sweep_off, reinterpret_cast<uint32_t*>(out), in.aug, S));
+    for (int cls = 1; cls < 4; ++cls) {
+        AugTileFrames fl;
+        fl.n = 0;
+        auto flush = [&]() -> int {
+            if (fl.n == 0) return 0;
+            const dim3 grid(kATBX * kATBY, S, fl.n);
+            switch (cls) {
+                case 1: BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, false><<<grid, kATThreads, AugTileCfg<true, false>::kSmem, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, out, in.aug, fl, S)); break;
+                case 2: BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<false, true><<<grid, kATThreads, AugTileCfg<false, true>::kSmem, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, out, in.aug, fl, S)); break;
+                default: BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, true><<<grid, kATThreads, AugTileCfg<true, true>::kSmem, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, out, in.aug, fl, S)); break;
+            }
+            fl.n = 0;
+            return 0;
+        };
+        for (int b = 0; b < B; ++b) {
+            if (cls_of(b) != cls) continue;
+            fl.src[fl.n] = fl.dst[fl.n] = (short)b;
+            if (++fl.n == 60) { const int rc = flush(); if (rc) return rc; }
+        }
+        const int rc = flush();
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // namespace
@@ -440,6 +543,26 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
 }  // namespace bevgen
 
 using namespace bevgen;
+
+extern "C" int bevgen_aug_fused_supported(const bevgen_aug_params* params_host, int B) {
+    if (!params_host || B < 0) return 0;
+    for (int b = 0; b < B; ++b)
+        if (!aug_tile_supported(params_host[b])) return 0;
+    return 1;
+}
+
+extern "C" int bevgen_lidar_bev_augmented(const void* pts, int pts_f16, const int32_t* sweep_offsets, const double* rel_tf,
+                                          int B, int S, int64_t total_points, int max_sweep_points,
+                                          const bevgen_aug_params* params, const bevgen_aug_params* params_host, float* out,
+                                          void* workspace, size_t workspace_bytes, bevgen_stream_t stream) {
+    if (total_points > 0 && (!pts || !rel_tf)) return BEVGEN_E_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(pts) & (pts_f16 ? 7u : 15u)) != 0) return BEVGEN_E_INVALID_ARG;
+    LidarIn in{pts_f16 ? static_cast<const uint2*>(pts) : nullptr, pts_f16 ? nullptr : static_cast<const float4*>(pts), rel_tf,
+               nullptr, nullptr, sweep_offsets, nullptr, nullptr, nullptr, S, params};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return pts_f16 ? launch_lidar_augmented<2>(in, B, S, total_points, max_sweep_points, params_host, out, workspace, workspace_bytes, st)
+                   : launch_lidar_augmented<0>(in, B, S, total_points, max_sweep_points, params_host, out, workspace, workspace_bytes, st);
+}
 
 extern "C" size_t bevgen_lidar_workspace_bytes(int64_t total_points, int B, int S) {
     if (total_points < 0 || B <= 0 || S <= 0) return 0;

@@ -1,0 +1,439 @@
+// lidar_aug_tile.cuh -- LiDAR generation FUSED with the resampling augmentations (rotate / scale), sm_100a.
+//
+// Replaces, for frames whose augmentation draw rotates and/or scales (reference utils.py:417-480), the sequence
+//   create_intentnet_lidar_bev (utils.py:62-106) -> np.flip (:399) -> 290 x cv2.warpAffine (:430-433)
+//   -> 290 x cv2.resize + crop/pad (:457-471) -> dropout rectangles (:496)
+// without ever materialising the un-augmented 334 MB grid: the dense two-pass path writes it, reads it back through a
+// 4-tap gather and writes the result (3 x 334 MB of HBM traffic per frame, LSU-bound); here the augmented grid is built
+// directly from the per-tile point records of k_bin_fixed and written ONCE.
+//
+// The un-augmented grid is > 99 % zeros, and an output pixel of a bilinear resampler is non-zero only if one of its taps
+// is.  One CTA owns one 40 x 72 output tile of one sweep and walks the sweep's 29 height channels:
+//   A  the point records of the <= 8 source row-bands under the tile's source footprint -> max into a shared-memory copy
+//      T0 of that footprint (the mirrored column of a flipped frame is already in the record)
+//   B  rotation: for every (record, one of 3 x 3 candidate destination pixels around the forward-mapped voxel) pair, in
+//      parallel over the CTA: if the pixel's cv2 fixed-point tap set really contains the voxel it is evaluated from T0
+//      with the reference's exact arithmetic (aug_geom.cuh).  Resize: the taps are separable and monotone, so an inverse
+//      tap table gives exactly the output rows / columns a source pixel feeds.  Results go into the shared output tile O;
+//      rotate + scale goes through an intermediate tile T1 (the rotated image's float32 rounding is part of the
+//      reference's result) whose non-zero pixels are listed as they are produced.
+//   C  O -> HBM (40 row pieces of 288 B, 16-byte stores; measured faster here than 40 small bulk copies), then only the
+//      touched entries of T0 / T1 are cleared again.
+// Geometry tables (warpAffine's X0/Y0/adelta/bdelta, resize taps and weights) are built once per CTA and reused for all
+// 29 channels.  Tiles whose source bands overflowed their fixed-capacity bins (dense scenes) also scan the sweep's
+// overflow list and fall back to scanning T0 for its non-zeros: slower, same bits.
+//
+// Included by lidar.cu INSIDE namespace bevgen::{anonymous}, after the tiled path's bin layout (kBinCap, kTilesPerSweep,
+// kTileElems, kFillRows, OvfRec); lidar.cu includes aug_geom.cuh at file scope first.
+#pragma once
+
+#include <type_traits>
+
+constexpr int kATW = 72, kATH = 40;                          // output tile (columns x rows): 288 B row pieces
+constexpr int kATBX = kW / kATW, kATBY = kH / kATH;          // 10 x 10 tiles per channel
+constexpr int kATElems = kATW * kATH;                        // 2880 floats
+constexpr int kATThreads = 256;
+constexpr int kATMaxBands = kATThreads / 32;                 // one warp per source row-band
+static_assert(kW % kATW == 0 && kH % kATH == 0, "tiles must cover the grid");
+static_assert((kATW * 4) % 16 == 0, "row pieces must be bulk-copy legal");
+
+template <bool ROT, bool SCL> struct AugTileCfg {
+    // capacities (floats); the host checks a conservative bound per frame (aug_tile_supported), the kernel traps beyond
+    static constexpr int kT0 = ROT ? (SCL ? 6400 : 5120) : 3840;   // source footprint
+    static constexpr int kT1 = (ROT && SCL) ? 3840 : 0;            // rotated intermediate (= the resize's source region)
+    static constexpr int kDW = SCL ? 80 : kATW;                    // rotation destination region (columns, rows)
+    static constexpr int kDH = SCL ? 48 : kATH;
+    static constexpr int kSmem = (kATElems + kT0 + kT1) * 4 + kT1 * 2;   // O, T0, T1, list of T1's non-zeros (u16)
+    static constexpr int kMinBlocks = (ROT && SCL) ? 3 : 4;
+};
+
+struct AugTileFrames {                                       // frames of one class, passed by value
+    int n;
+    short src[60], dst[60];                                  // frame index inside the binning launch (= params index), output slot
+};
+
+struct AugTileGeo {
+    int dx0, dy0, DW, DH;            // rotation destination region (ROT); == the resize source region when ROT && SCL
+    int qx0, qy0, QW, QH;            // resize source region (SCL)
+    int fx0, fy0, FW, FH;            // T0 footprint, clipped to the grid
+    int band0, nbands;
+};
+
+struct AugTileTables {
+    int X0[48], Y0[48], A[80], B[80];                        // warpAffine, over the rotation destination region
+    short s0x[kATW], s1x[kATW], s0y[kATH], s1y[kATH];        // resize taps per output column / row (s0 < 0: outside the image)
+    float wx0[kATW], wx1[kATW], wy0[kATH], wy1[kATH];
+    // inverse of the resize taps: source column qx0 + i feeds the output columns [xf[i], xl[i]] of the tile (taps are
+    // monotone, so it is a range; empty = (127, -1)); same for rows
+    int xf[80], xl[80], yf[48], yl[48];
+};
+
+// forward (source -> destination) map of the rotation; approximate, it only places the 3 x 3 candidate window
+struct RotFwd { float f00, f01, f02, f10, f11, f12, hx, hy; };
+constexpr int kATCand = 9;                                   // rotation candidates per source voxel (3 x 3; kernel traps unless hx, hy < 1.5)
+constexpr int kATRows = 3;                                   // resize: output rows per source pixel (<= 3 for scale factors < 1.45)
+constexpr int kATOrgBias = 64;
+
+// A work-list entry packs the voxel's footprint position (7 + 7 bits: the footprint is at most 127 x 127, checked) and,
+// for the rotation, the origin of its candidate window relative to the destination region (8 + 8 bits, biased).
+__device__ __forceinline__ uint32_t at_pack_pos(int fx, int fy) { return ((uint32_t)fy << 7) | (uint32_t)fx; }
+__device__ __forceinline__ int at_pos_x(uint32_t w) { return (int)(w & 127u); }
+__device__ __forceinline__ int at_pos_y(uint32_t w) { return (int)((w >> 7) & 127u); }
+__device__ __forceinline__ uint32_t rot_window_origin(int u, int v, const RotFwd& F, const AugTileGeo& G) {
+    const float cx = fmaf(F.f00, (float)u, fmaf(F.f01, (float)v, F.f02)), cy = fmaf(F.f10, (float)u, fmaf(F.f11, (float)v, F.f12));
+    const int xr = min(max((int)ceilf(cx - F.hx) - G.dx0 + kATOrgBias, 0), 255);   // clamped windows lie outside the region
+    const int yr = min(max((int)ceilf(cy - F.hy) - G.dy0 + kATOrgBias, 0), 255);
+    return ((uint32_t)yr << 22) | ((uint32_t)xr << 14);
+}
+
+// Candidate c (0..8) of the source voxel of work-list entry w (position + window origin): if that
+// destination pixel's 4 cv2 taps include the voxel, evaluate it from T0 with the reference's arithmetic.  TO_OUT: D is the
+// output tile (dropout rectangles apply); otherwise D is the rotated intermediate T1 and its non-zero pixels are
+// appended (once each) to the list W2.
+template <bool TO_OUT>
+__device__ __forceinline__ void rot_candidate(uint32_t w_, int c, const AugTileGeo& G, const AugTileTables& T,
+                                              const float* __restrict__ T0, float* __restrict__ D, const int* rects, int nrect,
+                                              uint16_t* __restrict__ W2, uint32_t* nW2) {
+    const int cyi = c / 3, cxi = c - 3 * cyi;
+    const int lx = (int)((w_ >> 14) & 255u) - kATOrgBias + cxi, ly = (int)(w_ >> 22) - kATOrgBias + cyi;
+    if ((unsigned)lx >= (unsigned)G.DW || (unsigned)ly >= (unsigned)G.DH) return;
+    const int X = (T.X0[ly] + T.A[lx]) >> 5, Y = (T.Y0[ly] + T.B[lx]) >> 5;
+    const int ix = (X >> 5) - G.fx0, iy = (Y >> 5) - G.fy0;                 // top-left tap, footprint coordinates
+    const int fx = at_pos_x(w_), fy = at_pos_y(w_);
+    if ((unsigned)(fx - ix) > 1u || (unsigned)(fy - iy) > 1u) return;       // the voxel is not one of this pixel's taps
+    if (TO_OUT && nrect && in_rects(rects, nrect, G.dy0 + ly, G.dx0 + lx)) return;              // utils.py:496
+    float w[4];
+    rot_weights(X, Y, w);
+    // taps outside the (grid-clipped) footprint are outside the grid: BORDER_CONSTANT 0
+    const bool x0ok = (unsigned)ix < (unsigned)G.FW, x1ok = (unsigned)(ix + 1) < (unsigned)G.FW;
+    const bool y0ok = (unsigned)iy < (unsigned)G.FH, y1ok = (unsigned)(iy + 1) < (unsigned)G.FH;
+    const float* p = T0 + iy * G.FW + ix;
+    const float v00 = (x0ok && y0ok) ? p[0] : 0.f, v01 = (x1ok && y0ok) ? p[1] : 0.f;
+    const float v10 = (x0ok && y1ok) ? p[G.FW] : 0.f, v11 = (x1ok && y1ok) ? p[G.FW + 1] : 0.f;
+    const float val = rot_sum(v00, v01, v10, v11, w);
+    const int di = ly * G.DW + lx;
+    if (TO_OUT) { D[di] = val; return; }
+    // every writer of a pixel writes the same value; the one that finds it still zero lists it (a pixel whose value
+    // is zero needs no further work: it equals an untouched one)
+    const uint32_t old = atomicExch(reinterpret_cast<uint32_t*>(D) + di, __float_as_uint(val));
+    if (old == 0u && __float_as_uint(val) != 0u) W2[atomicAdd(nW2, 1u)] = (uint16_t)di;
+}
+
+// Source pixel (u, v) of the resize (coordinates of the image being resized), r-th of the output rows it feeds: evaluate
+// every output pixel of that row whose 2 x 2 taps include it (exactly the columns [xf, xl] of the inverse tap table).
+// src = tile holding the region [qx0, qx0+QW) x [qy0, qy0+QH), row stride QW.
+__device__ __forceinline__ void scl_row(int u, int v, int r, const AugTileGeo& G, const AugTileTables& T,
+                                        const float* __restrict__ src, float* __restrict__ O, int ox0, int oy0,
+                                        const int* rects, int nrect) {
+    const int ly = T.yf[v - G.qy0] + r;
+    if (ly > T.yl[v - G.qy0]) return;
+    const int x0 = T.xf[u - G.qx0], x1 = T.xl[u - G.qx0];
+    const int b0 = T.s0y[ly], b1 = T.s1y[ly];
+    const float wy0 = T.wy0[ly], wy1 = T.wy1[ly];
+    const float* r0 = src + (b0 - G.qy0) * G.QW - G.qx0;
+    const float* r1 = src + (b1 - G.qy0) * G.QW - G.qx0;
+    for (int lx = x0; lx <= x1; ++lx) {
+        if (nrect && in_rects(rects, nrect, oy0 + ly, ox0 + lx)) continue;                      // utils.py:496
+        const int a0 = T.s0x[lx], a1 = T.s1x[lx];
+        O[ly * kATW + lx] = resize_sum(r0[a0], r0[a1], r1[a0], r1[a1], T.wx0[lx], T.wx1[lx], wy0, wy1);
+    }
+}
+
+template <bool ROT, bool SCL>
+__global__ void __launch_bounds__(kATThreads, AugTileCfg<ROT, SCL>::kMinBlocks)
+k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, const uint32_t* __restrict__ ovf_cnt,
+           const OvfRec* __restrict__ ovf, const int32_t* __restrict__ sweep_off, float* __restrict__ out,
+           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S) {
+    static_assert(ROT || SCL, "frames that neither rotate nor scale go through k_tile_store");
+    using Cfg = AugTileCfg<ROT, SCL>;
+    extern __shared__ __align__(128) unsigned char at_smem[];
+    float* const O = reinterpret_cast<float*>(at_smem);
+    float* const T0 = O + kATElems;
+    float* const T1 = T0 + Cfg::kT0;
+    uint16_t* const W2 = reinterpret_cast<uint16_t*>(T1 + Cfg::kT1);   // indices of T1's non-zeros (ROT && SCL)
+    __shared__ bevgen_aug_params P;
+    __shared__ AugTileTables T;
+    __shared__ AugTileGeo G;
+    __shared__ RotFwd RF;
+    __shared__ uint32_t W[kATMaxBands * kBinCap];            // this channel's in-footprint records (at_pack_pos | rot_window_origin)
+    __shared__ uint32_t nW, nW2;
+    __shared__ uint2 Rs[kATMaxBands * kBinCap];              // staging of the NEXT channel's records (cp.async, thread-private slots)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bx = blockIdx.x % kATBX, by = blockIdx.x / kATBX, sweep = blockIdx.y;
+    const int fsrc = fl.src[blockIdx.z], fdst = fl.dst[blockIdx.z];
+    const int ox0 = bx * kATW, oy0 = by * kATH;
+    {
+        const int* g = reinterpret_cast<const int*>(params + fsrc);
+        int* s = reinterpret_cast<int*>(&P);
+        for (int i = tid; i < (int)(sizeof(bevgen_aug_params) / 4); i += kATThreads) s[i] = g[i];
+    }
+    if (SCL && tid < 80) { T.xf[tid] = 127; T.xl[tid] = -1; if (tid < 48) { T.yf[tid] = 127; T.yl[tid] = -1; } }
+    __syncthreads();
+    int nrect = P.n_rects;
+    nrect = nrect > kMaxRects ? kMaxRects : (nrect < 0 ? 0 : nrect);
+
+    // ---- geometry, once per CTA ---------------------------------------------------------------------------------
+    if (SCL) {
+        const ScalePlacement pl = scale_placement(P.scale);
+        if (tid < kATW + kATH) {
+            const bool col = tid < kATW;
+            const int l = col ? tid : tid - kATW;
+            const int o = col ? ox0 + l : oy0 + l, off = col ? pl.w0 : pl.h0, n = col ? pl.nw : pl.nh;
+            const int r = pl.crop ? o + off : o - off;
+            int s0 = -1, s1 = -1;
+            float w0 = 0.f, w1 = 0.f;
+            if (r >= 0 && r < n) resize_tap(r, n, col ? kW : kH, s0, s1, w0, w1);
+            if (col) { T.s0x[l] = (short)s0; T.s1x[l] = (short)s1; T.wx0[l] = w0; T.wx1[l] = w1; }
+            else     { T.s0y[l] = (short)s0; T.s1y[l] = (short)s1; T.wy0[l] = w0; T.wy1[l] = w1; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // valid columns / rows are contiguous; taps are monotone, so the region is [first s0, last s1]
+            int c0 = 0, c1 = kATW - 1, r0 = 0, r1 = kATH - 1;
+            while (c0 <= c1 && T.s0x[c0] < 0) ++c0;
+            while (c1 >= c0 && T.s0x[c1] < 0) --c1;
+            while (r0 <= r1 && T.s0y[r0] < 0) ++r0;
+            while (r1 >= r0 && T.s0y[r1] < 0) --r1;
+            if (c0 > c1 || r0 > r1) { G.qx0 = G.qy0 = 0; G.QW = G.QH = 0; }
+            else { G.qx0 = T.s0x[c0]; G.QW = T.s1x[c1] - G.qx0 + 1; G.qy0 = T.s0y[r0]; G.QH = T.s1y[r1] - G.qy0 + 1; }
+            if (ROT) { G.dx0 = G.qx0; G.dy0 = G.qy0; G.DW = G.QW; G.DH = G.QH; }
+            else { G.fx0 = G.qx0; G.fy0 = G.qy0; G.FW = G.QW; G.FH = G.QH; }
+        }
+        __syncthreads();
+        if (G.QW > 80 || G.QH > 48) __trap();
+        // inverse tap tables: which output columns / rows of the tile read source column / row i
+        if (tid < kATW + kATH && G.QW > 0) {
+            const bool col = tid < kATW;
+            const int l = col ? tid : tid - kATW;
+            const int s0 = col ? T.s0x[l] : T.s0y[l], s1 = col ? T.s1x[l] : T.s1y[l];
+            if (s0 >= 0) {
+                int* f = col ? T.xf : T.yf;
+                int* la = col ? T.xl : T.yl;
+                const int q0 = col ? G.qx0 : G.qy0;
+                atomicMin(f + s0 - q0, l); atomicMax(la + s0 - q0, l);
+                atomicMin(f + s1 - q0, l); atomicMax(la + s1 - q0, l);
+            }
+        }
+    } else if (tid == 0) {
+        G.dx0 = ox0; G.dy0 = oy0; G.DW = kATW; G.DH = kATH;
+    }
+    __syncthreads();
+    if (ROT) {
+        if (G.DW > Cfg::kDW || G.DH > Cfg::kDH) __trap();
+        if (tid < G.DW) { T.A[tid] = rot_adelta(P.minv, G.dx0 + tid); T.B[tid] = rot_bdelta(P.minv, G.dx0 + tid); }
+        else if (tid >= 128 && tid - 128 < G.DH) { T.X0[tid - 128] = rot_X0(P.minv, G.dy0 + tid - 128); T.Y0[tid - 128] = rot_Y0(P.minv, G.dy0 + tid - 128); }
+        if (tid == 255) {
+            // forward (src -> dst) map = inverse of minv; float is ample: it only places the candidate window
+            const double a = P.minv[0], b = P.minv[1], c = P.minv[2], d = P.minv[3], e = P.minv[4], f = P.minv[5];
+            const double det = a * e - b * d, id = det != 0.0 ? 1.0 / det : 0.0;
+            RF.f00 = (float)(e * id); RF.f01 = (float)(-b * id); RF.f10 = (float)(-d * id); RF.f11 = (float)(a * id);
+            RF.f02 = (float)(-(e * id * c - b * id * f)); RF.f12 = (float)(-(-d * id * c + a * id * f));
+            // |dst - centre| <= |F| * 1.02 (taps within +-1 of the voxel, plus the fixed-point rounding of the coordinates)
+            RF.hx = (fabsf(RF.f00) + fabsf(RF.f01)) * 1.03f + 0.05f;
+            RF.hy = (fabsf(RF.f10) + fabsf(RF.f11)) * 1.03f + 0.05f;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (G.DW <= 0 || G.DH <= 0) { G.fx0 = G.fy0 = 0; G.FW = G.FH = 0; }
+            else {
+                // X0(y) and adelta(x) are monotone: the extremes sit at the region's corners
+                const int xa = min(T.X0[0], T.X0[G.DH - 1]) + min(T.A[0], T.A[G.DW - 1]);
+                const int xb = max(T.X0[0], T.X0[G.DH - 1]) + max(T.A[0], T.A[G.DW - 1]);
+                const int ya = min(T.Y0[0], T.Y0[G.DH - 1]) + min(T.B[0], T.B[G.DW - 1]);
+                const int yb = max(T.Y0[0], T.Y0[G.DH - 1]) + max(T.B[0], T.B[G.DW - 1]);
+                const int fx0 = max(xa >> 10, 0), fx1 = min((xb >> 10) + 1, kW - 1);
+                const int fy0 = max(ya >> 10, 0), fy1 = min((yb >> 10) + 1, kH - 1);
+                if (fx1 < fx0 || fy1 < fy0) { G.fx0 = G.fy0 = 0; G.FW = G.FH = 0; }
+                else { G.fx0 = fx0; G.fy0 = fy0; G.FW = fx1 - fx0 + 1; G.FH = fy1 - fy0 + 1; }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        G.band0 = G.fy0 / kFillRows;
+        G.nbands = (G.FW > 0 && G.FH > 0) ? (G.fy0 + G.FH - 1) / kFillRows - G.band0 + 1 : 0;
+        nW = 0; nW2 = 0;
+    }
+    __syncthreads();
+    const int FW = G.FW, FH = G.FH, fx0 = G.fx0, fy0 = G.fy0;
+    if (FW * FH > Cfg::kT0 || FW > 127 || FH > 127 || G.nbands > kATMaxBands || (ROT && SCL && G.DW * G.DH > Cfg::kT1)) __trap();
+    if (ROT && (RF.hx >= 1.5f || RF.hy >= 1.5f)) __trap();
+    if (SCL && tid < G.QW && T.xl[tid] - T.xf[tid] >= 8) __trap();           // (never for scale factors anywhere near 1)
+    if (SCL && tid < G.QH && T.yl[tid] - T.yf[tid] >= kATRows) __trap();
+    for (int i = tid; i < (kATElems + Cfg::kT0 + Cfg::kT1) / 4; i += kATThreads) reinterpret_cast<float4*>(at_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // ---- per-band record counts of all 29 channels: lane z of warp w holds cnt[z][band0 + w] ---------------------
+    const int bs = fsrc * S + sweep;
+    const int band = G.band0 + warp;
+    const bool has_band = warp < G.nbands;
+    uint32_t c_reg = 0;
+    if (has_band && lane < kZ) c_reg = __ldg(cnt + (size_t)bs * kTilesPerSweep + lane * (kH / kFillRows) + band);
+    constexpr int kBinStrideZ = (kH / kFillRows) * kBinCap;  // records between consecutive channels of one band
+
+    // records of channel z, this warp's band: <= 4 per lane, fetched one channel ahead straight into shared memory
+    // (cp.async: no registers held across the stages, nothing waits on the load until the next channel starts);
+    // each thread reads back only the slots it filled itself, so its own wait_group is all the ordering needed
+    uint2* const rs = Rs + warp * kBinCap + lane;
+    const uint2* binp = bins + ((size_t)bs * kTilesPerSweep + band) * kBinCap + lane;
+    auto load_records = [&](int z, uint32_t& n, bool& over) {
+        const uint32_t n_all = __shfl_sync(0xFFFFFFFFu, c_reg, z);
+        over = n_all > (uint32_t)kBinCap;
+        n = over ? (uint32_t)kBinCap : n_all;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((uint32_t)(lane + 32 * k) < n) cp_async_8(rs + 32 * k, binp + 32 * k);
+        cp_async_commit();
+        binp += kBinStrideZ;
+    };
+    uint32_t n = 0;
+    bool over = false;
+    load_records(0, n, over);
+    // this thread's float4s of the output tile: piece j = tid + 256 j (< 720): row j / 18, 16-byte column j % 18
+    constexpr int kPieces = (kATElems / 4 + kATThreads - 1) / kATThreads;        // 3
+    uint32_t goff[kPieces];
+#pragma unroll
+    for (int j = 0; j < kPieces; ++j) {
+        const int i = tid + j * kATThreads, r = i / (kATW / 4);
+        goff[j] = (uint32_t)(r * kW + (i - r * (kATW / 4)) * 4);
+    }
+    float* oplane = out + ((size_t)(fdst * S + sweep) * kZ) * kPlane + (size_t)oy0 * kW + ox0;
+    __syncthreads();
+
+#pragma unroll 1
+    for (int z = 0; z < kZ; ++z, oplane += kPlane) {
+        // ---- A: records -> T0 (max), in-footprint records -> work list W (one shared atomic per warp) ----------------
+        cp_async_wait_all();
+        if (n) {                                             // warp-uniform
+            uint32_t word[4], m[4], total = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                word[k] = 0xFFFFFFFFu;
+                if ((uint32_t)(lane + 32 * k) < n) {
+                    const uint2 rec = rs[32 * k];
+                    const int r = (int)(rec.x / (uint32_t)kW), col = (int)rec.x - r * kW;
+                    const int fx = col - fx0, fy = band * kFillRows + r - fy0;
+                    if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH) {
+                        atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, rec.y);
+                        word[k] = at_pack_pos(fx, fy);
+                        if (ROT) word[k] |= rot_window_origin(fx0 + fx, fy0 + fy, RF, G);
+                    }
+                }
+                m[k] = __ballot_sync(0xFFFFFFFFu, word[k] != 0xFFFFFFFFu);
+                total += (uint32_t)__popc(m[k]);
+            }
+            if (total) {                                     // one shared atomic per warp claims the slots of all its records
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&nW, total);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (word[k] != 0xFFFFFFFFu) W[base + __popc(m[k] & ((1u << lane) - 1u))] = word[k];
+                    base += (uint32_t)__popc(m[k]);
+                }
+            }
+        }
+        const bool slow = __syncthreads_or(over) != 0;      // uniform: some source band of this channel overflowed its bin
+        if (z + 1 < kZ) load_records(z + 1, n, over);         // next channel's records: latency hidden behind B and C
+        if (slow) {
+            const uint32_t n_ovf = ovf_cnt[bs];
+            const OvfRec* list = ovf + (sweep_off[bs] - sweep_off[0]);
+            for (uint32_t i = tid; i < n_ovf; i += kATThreads) {
+                const OvfRec r = list[i];
+                const uint32_t tile = (uint32_t)(r.idx / kTileElems), cell = (uint32_t)(r.idx - (unsigned long long)tile * kTileElems);
+                const uint32_t bin_id = tile - (uint32_t)bs * kTilesPerSweep;
+                if ((int)(bin_id / (kH / kFillRows)) != z) continue;
+                const int rr = (int)(cell / (uint32_t)kW), col = (int)cell - rr * kW;
+                const int fx = col - fx0, fy = (int)(bin_id % (kH / kFillRows)) * kFillRows + rr - fy0;
+                if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH)
+                    atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, r.bits);
+            }
+            __syncthreads();
+        }
+        // ---- B: every non-zero source voxel -> the destination pixels it feeds -----------------------------------------
+        const uint32_t nw = nW;
+        if (ROT) {
+            float* const D = SCL ? T1 : O;
+            if (!slow) {
+                for (uint32_t i = tid; i < nw * kATCand; i += kATThreads) {
+                    const uint32_t r = i / kATCand;
+                    rot_candidate<!SCL>(W[r], (int)(i - r * kATCand), G, T, T0, D, P.rects, nrect, W2, &nW2);
+                }
+            } else {
+                for (int i = tid; i < FW * FH; i += kATThreads)
+                    if (__float_as_uint(T0[i]) != 0u) {
+                        const int fy = i / FW, fx = i - fy * FW;
+                        const uint32_t w = at_pack_pos(fx, fy) | rot_window_origin(fx0 + fx, fy0 + fy, RF, G);
+                        for (int c = 0; c < kATCand; ++c) rot_candidate<!SCL>(w, c, G, T, T0, D, P.rects, nrect, W2, &nW2);
+                    }
+            }
+        } else {
+            if (!slow) {
+                for (uint32_t i = tid; i < nw * kATRows; i += kATThreads) {
+                    const uint32_t r = i / kATRows, w = W[r];
+                    scl_row(fx0 + at_pos_x(w), fy0 + at_pos_y(w), (int)(i - r * kATRows), G, T, T0, O, ox0, oy0, P.rects, nrect);
+                }
+            } else {
+                for (int i = tid; i < FW * FH; i += kATThreads)
+                    if (__float_as_uint(T0[i]) != 0u)
+                        for (int r = 0; r < kATRows; ++r) scl_row(fx0 + i % FW, fy0 + i / FW, r, G, T, T0, O, ox0, oy0, P.rects, nrect);
+            }
+        }
+        uint32_t nw2 = 0;
+        if (ROT && SCL) {
+            __syncthreads();
+            nw2 = nW2;                                        // T1's non-zero pixels, each listed once
+            for (uint32_t i = tid; i < nw2 * kATRows; i += kATThreads) {
+                const uint32_t r = i / kATRows;
+                const int q = W2[r], qy = q / G.DW;
+                scl_row(G.dx0 + q - qy * G.DW, G.dy0 + qy, (int)(i - r * kATRows), G, T, T1, O, ox0, oy0, P.rects, nrect);
+            }
+        }
+        __syncthreads();
+        // ---- C: O -> HBM (each thread re-zeroes the float4s it has just read), clear the touched entries of T0 / T1 ------
+#pragma unroll
+        for (int j = 0; j < kPieces; ++j) {
+            const int i = tid + j * kATThreads;
+            if (i < kATElems / 4) {
+                const float4 val = reinterpret_cast<const float4*>(O)[i];
+                reinterpret_cast<float4*>(O)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __stcs(reinterpret_cast<float4*>(oplane + goff[j]), val);
+            }
+        }
+        if (!slow) {
+            for (uint32_t i = tid; i < nw; i += kATThreads) { const uint32_t w = W[i]; T0[at_pos_y(w) * FW + at_pos_x(w)] = 0.f; }
+            if (ROT && SCL)
+                for (uint32_t i = tid; i < nw2; i += kATThreads) T1[W2[i]] = 0.f;
+        } else {
+            for (int i = tid; i < (Cfg::kT0 + Cfg::kT1) / 4; i += kATThreads) reinterpret_cast<float4*>(T0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (tid == 0) { nW = 0; nW2 = 0; }                   // every thread took its copies (nw, nw2) before the barrier above
+        __syncthreads();
+    }
+}
+
+// Host: can k_tile_aug handle this frame's parameters?  Conservative real-valued bounds on the region sizes the kernel
+// derives exactly (the reference's own draws -- |angle| <= 15 degrees, 0.95 <= scale <= 1.05 -- always pass).
+inline bool aug_tile_supported(const bevgen_aug_params& p) {
+    const bool rot = p.do_rotate != 0, scl = p.do_scale != 0;
+    if (!rot && !scl) return true;
+    auto bands_ok = [](int fh) { return (fh + kFillRows - 2) / kFillRows + 1 <= kATMaxBands; };   // fh rows span at most this many bands
+    double dw = kATW, dh = kATH;
+    if (scl) {
+        if (!(p.scale > 0.25 && p.scale < 4.0)) return false;
+        const double sf = (double)(int)(kW * p.scale) / kW, sg = (double)(int)(kH * p.scale) / kH;
+        if (!(sf > 0.0 && sg > 0.0)) return false;
+        dw = kATW / sf + 3.0; dh = kATH / sg + 3.0;                       // resize source region of one tile
+        const int qw = (int)dw + 1, qh = (int)dh + 1;
+        if (!rot) return qw * qh <= AugTileCfg<false, true>::kT0 && bands_ok(qh);
+        if (qw > AugTileCfg<true, true>::kDW || qh > AugTileCfg<true, true>::kDH || qw * qh > AugTileCfg<true, true>::kT1) return false;
+    }
+    for (int k = 0; k < 6; ++k) if (!(p.minv[k] == p.minv[k]) || fabs(p.minv[k]) > 1e6) return false;
+    const double det = p.minv[0] * p.minv[4] - p.minv[1] * p.minv[3];
+    if (!(fabs(det) > 0.25 && fabs(det) < 4.0)) return false;
+    // source footprint of the rotation's destination region (+2 for the taps, +2 slack for the fixed-point rounding)
+    const int fw = (int)(fabs(p.minv[0]) * (dw - 1) + fabs(p.minv[1]) * (dh - 1) + 4.0) + 1;
+    const int fh = (int)(fabs(p.minv[3]) * (dw - 1) + fabs(p.minv[4]) * (dh - 1) + 4.0) + 1;
+    return fw * fh <= (scl ? AugTileCfg<true, true>::kT0 : AugTileCfg<true, false>::kT0) && bands_ok(fh);
+}
+

@@ -98,10 +98,13 @@ class BevGenerator:
     """Owns the device-side state (map table, workspaces) and turns FrameBatches into model inputs."""
 
     def __init__(self, map_table: Optional[map_ops.MapTable] = None, algo: int = bev_ops.ALGO_TILED,
-                 device: Optional[torch.device] = None) -> None:
+                 device: Optional[torch.device] = None, fused_augment: bool = True) -> None:
         self.device = device or bev_ops._require_cuda()
         self.map_table = map_table
         self.algo = algo
+        # LiDAR frames that rotate / scale: built directly in augmented form from the binned point records (one write of
+        # the grid) instead of generate -> gather (three passes over it).  Tiled algorithm only; same bits either way.
+        self.fused_augment = fused_augment
         self._scratch = {}
         # the map rasterizer is independent of the LiDAR kernels and far from saturating the GPU (one warp per lane
         # segment): it runs on a side stream and is joined before the tensors are handed out
@@ -169,7 +172,27 @@ class BevGenerator:
         main = torch.cuda.current_stream()
         if with_map:
             self._map_stream.wait_stream(main)          # inputs (uploads, fusion arrays) are ready on the main stream
-        if J == 0:
+        if J and self.fused_augment and self.algo == bev_ops.ALGO_TILED and _aug.fused_supported(aug):
+            # LiDAR: one pass for the whole batch, whatever the frame order (no partition needed)
+            _aug.lidar_bev_augmented(dv["points4"], dv["sweep_offsets"], dv["rel_tf"], B, S, aug,
+                                     max_sweep_points=batch.max_sweep_points, out=out_lidar)
+            if with_map:
+                # map: 3 % of the bytes -- dense route (raster into scratch, gather) for the frames that resample
+                with torch.cuda.stream(self._map_stream):
+                    need_idx = [i for i, nd in enumerate(need) if nd]
+                    lo, hi = need_idx[0], need_idx[-1] + 1          # contiguous [0, J) when partitioned
+                    gen_m = self._buf("gen_m", (hi - lo,) + mshape[1:])
+                    sl = slice(lo, hi)
+                    map_ops.rasterize_maps(self.map_table, ids[sl], d_T[sl], flip=d_flip[sl], drop_rects=d_rects[sl],
+                                           drop_counts=d_cnt[sl], out=gen_m)
+                    gp = [p if p.needs_gather else _aug.AugParams() for p in aug[lo:hi]]
+                    _aug.augment_grid(gen_m, gp, out=out_map[sl])
+                    for a, b in ((0, lo), (hi, B)):
+                        if b > a:
+                            s2 = slice(a, b)
+                            map_ops.rasterize_maps(self.map_table, ids[s2], d_T[s2], flip=d_flip[s2], drop_rects=d_rects[s2],
+                                                   drop_counts=d_cnt[s2], out=out_map[s2])
+        elif J == 0:
             run(0, B, out_lidar, out_map)
         else:
             gen_l = self._buf("gen_l", (J,) + lshape[1:])
