@@ -361,7 +361,7 @@ def run_ours(args) -> None:
         "k_zero_fill_tma": LIDAR_FRAME_BYTES, "cudaMemsetAsync": LIDAR_FRAME_BYTES, "k_scatter_atomic": pts_frame * 16,
         "k_bin_fixed": pts_frame * 16, "k_tile_store": LIDAR_FRAME_BYTES, "k_overflow_red": 0,
         "k_map_expand": MAP_FRAME_BYTES, "k_augment": 2 * (LIDAR_FRAME_BYTES + (MAP_FRAME_BYTES if wl["map"] else 0)),
-        "k_tile_aug": LIDAR_FRAME_BYTES,
+        "k_tile_aug": LIDAR_FRAME_BYTES, "k_rebin_aug": 0,
     }
     n_gather = sum(1 for p in (aug or []) if p.needs_gather)
     fused_aug = bool(aug) and "k_tile_aug" in kernels

@@ -175,12 +175,14 @@ int bevgen_augment(const float *src, float *dst, int B, int C, const bevgen_aug_
  * scratch grid, then bevgen_augment -- moves 3x the bytes).  Same bits as that route.
  *   pts / pts_f16   float32 [N,4] (pts_f16 = 0) or 4 x fp16 per point (pts_f16 = 1); sweep_offsets, rel_tf as above
  *   params          device array of B bevgen_aug_params; params_host = the same structs in host memory
- *   workspace       bevgen_lidar_workspace_bytes(total_points, B, S)
+ *   workspace       bevgen_lidar_aug_workspace_bytes(total_points, B, S, n_resampled), n_resampled = number of
+ *                   frames with do_rotate or do_scale (59 MB of per-tile record bins per such frame at S = 10)
  * Returns BEVGEN_E_UNSUPPORTED when a frame's parameters are outside what the fused kernel's shared-memory tiles
  * cover (never for the reference's own draws: |angle| <= 15 deg, 0.95 <= scale <= 1.05); query first with
  * bevgen_aug_fused_supported (1 = every frame supported) and take the dense route otherwise.
  * ------------------------------------------------------------------------------------- */
 int bevgen_aug_fused_supported(const bevgen_aug_params *params_host, int B);
+size_t bevgen_lidar_aug_workspace_bytes(int64_t total_points, int B, int S, int n_resampled);
 
 int bevgen_lidar_bev_augmented(const void *pts, int pts_f16, const int32_t *sweep_offsets, const double *rel_tf,
                                int B, int S, int64_t total_points, int max_sweep_points,

@@ -184,7 +184,7 @@ def lidar_bev_augmented(points4: torch.Tensor, sweep_offsets: torch.Tensor, rel_
     dparams = _dev(hparams, torch.uint8, device)
     L = _native.lib()
     n = int(pts.shape[0])
-    wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
+    wbytes = int(L.bevgen_lidar_aug_workspace_bytes(n, B, S, sum(1 for p in params if p.needs_gather)))
     ws = workspace.get("lidar", wbytes, device)
     rc = L.bevgen_lidar_bev_augmented(_ptr(pts), 1 if pts.dtype == torch.float16 else 0, _ptr(off), _ptr(tf), B, S, n,
                                       int(max_sweep_points), _ptr(dparams), C.c_void_p(hparams.ctypes.data), _ptr(out),

@@ -386,16 +386,20 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // workspace of the tiled algorithm: [cnt u32 per tile | ovf_cnt] [bins: kBinCap records per tile] [overflow list]
 struct TiledWorkspace {
-    size_t cnt, bins, ovf, bytes;
+    size_t cnt, bins, ovf, cnt2, bins2, bytes;
 };
 
-TiledWorkspace tiled_layout(long long total_points, int B, int S) {
+// n_resampled > 0 adds the per-(channel, output tile) bins of the fused generation+augmentation path (lidar_aug_tile.cuh)
+TiledWorkspace tiled_layout(long long total_points, int B, int S, int n_resampled = 0) {
     TiledWorkspace w;
     const size_t ntiles = (size_t)B * S * kTilesPerSweep;
     size_t off = 0;
     w.cnt = off;  off += align_up((ntiles + (size_t)B * S + 64) * 4, 256);      // per-tile counts, then per-sweep overflow counts
     w.bins = off; off += align_up(ntiles * kBinCap * sizeof(uint2), 256);
     w.ovf = off;  off += align_up((size_t)total_points * sizeof(OvfRec), 256);
+    const size_t nbins2 = (size_t)n_resampled * S * kZ * 100;
+    w.cnt2 = off;  off += align_up(nbins2 * 4, 256);
+    w.bins2 = off; off += align_up(nbins2 * 256 * sizeof(uint2), 256);
     w.bytes = off;
     return w;
 }
@@ -471,15 +475,21 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
     if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
     const size_t ntiles = (size_t)B * S * kTilesPerSweep;
     if (ntiles > 0x7FFFFFFFull || (unsigned)(B * S) > 65535u || B > 32767) return BEVGEN_E_UNSUPPORTED;
-    for (int b = 0; b < B; ++b)
+    int n_resampled = 0;
+    for (int b = 0; b < B; ++b) {
         if (!aug_tile_supported(params_host[b])) return BEVGEN_E_UNSUPPORTED;
-    const TiledWorkspace L = tiled_layout(total_points, B, S);
+        n_resampled += (params_host[b].do_rotate != 0 || params_host[b].do_scale != 0) ? 1 : 0;
+    }
+    static_assert(kATTiles == 100 && kATCap == 256, "tiled_layout sizes the per-tile bins");
+    const TiledWorkspace L = tiled_layout(total_points, B, S, n_resampled);
     if (!workspace || workspace_bytes < L.bytes) return BEVGEN_E_WORKSPACE;
     char* wp = static_cast<char*>(workspace);
     uint32_t* cnt = reinterpret_cast<uint32_t*>(wp + L.cnt);
     uint32_t* ovf_cnt = cnt + ntiles;
     uint2* bins = reinterpret_cast<uint2*>(wp + L.bins);
     OvfRec* ovf = reinterpret_cast<OvfRec*>(wp + L.ovf);
+    uint32_t* cnt2 = reinterpret_cast<uint32_t*>(wp + L.cnt2);
+    uint2* bins2 = reinterpret_cast<uint2*>(wp + L.bins2);
     BEVGEN_CUDA(cudaMemsetAsync(cnt, 0, (ntiles + (size_t)B * S + 64) * 4, st));
     static bool attr_set[3] = {false, false, false};
     if (!attr_set[MODE]) {
@@ -513,16 +523,29 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
     if (any_plain && have_points)
         BEVGEN_LAUNCH("k_overflow_red", st, k_overflow_red<<<dim3(kOvfCtas, B * S), 256, 0, st>>>(
                           ovf_cnt, ovf, in.sweep_off, reinterpret_cast<uint32_t*>(out), in.aug, S));
+    int next_slot = 0;
     for (int cls = 1; cls < 4; ++cls) {
         AugTileFrames fl;
         fl.n = 0;
         auto flush = [&]() -> int {
             if (fl.n == 0) return 0;
-            const dim3 grid(kATBX * kATBY, S, fl.n);
+            const dim3 rgrid(kZ, S, fl.n), grid(kATTiles, S, fl.n);
             switch (cls) {
-                case 1: BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, false><<<grid, kATThreads, AugTileCfg<true, false>::kSmem, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, out, in.aug, fl, S)); break;
-                case 2: BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<false, true><<<grid, kATThreads, AugTileCfg<false, true>::kSmem, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, out, in.aug, fl, S)); break;
-                default: BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, true><<<grid, kATThreads, AugTileCfg<true, true>::kSmem, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, out, in.aug, fl, S)); break;
+                case 1:
+                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, false><<<rgrid, kATThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
+                    BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, false><<<grid, kATThreads, AugTileCfg<true, false>::kSmem, st>>>(
+                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
+                    break;
+                case 2:
+                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<false, true><<<rgrid, kATThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
+                    BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<false, true><<<grid, kATThreads, AugTileCfg<false, true>::kSmem, st>>>(
+                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
+                    break;
+                default:
+                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, true><<<rgrid, kATThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
+                    BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, true><<<grid, kATThreads, AugTileCfg<true, true>::kSmem, st>>>(
+                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
+                    break;
             }
             fl.n = 0;
             return 0;
@@ -530,6 +553,7 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
         for (int b = 0; b < B; ++b) {
             if (cls_of(b) != cls) continue;
             fl.src[fl.n] = fl.dst[fl.n] = (short)b;
+            fl.slot[fl.n] = (short)next_slot++;
             if (++fl.n == 60) { const int rc = flush(); if (rc) return rc; }
         }
         const int rc = flush();
@@ -543,6 +567,11 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
 }  // namespace bevgen
 
 using namespace bevgen;
+
+extern "C" size_t bevgen_lidar_aug_workspace_bytes(int64_t total_points, int B, int S, int n_resampled) {
+    if (total_points < 0 || B <= 0 || S <= 0 || n_resampled < 0 || n_resampled > B) return 0;
+    return tiled_layout(total_points, B, S, n_resampled).bytes;
+}
 
 extern "C" int bevgen_aug_fused_supported(const bevgen_aug_params* params_host, int B) {
     if (!params_host || B < 0) return 0;

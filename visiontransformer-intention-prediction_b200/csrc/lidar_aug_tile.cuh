@@ -5,37 +5,45 @@
 //   -> 290 x cv2.resize + crop/pad (:457-471) -> dropout rectangles (:496)
 // without ever materialising the un-augmented 334 MB grid: the dense two-pass path writes it, reads it back through a
 // 4-tap gather and writes the result (3 x 334 MB of HBM traffic per frame, LSU-bound); here the augmented grid is built
-// directly from the per-tile point records of k_bin_fixed and written ONCE.
+// directly from the point records of k_bin_fixed and written ONCE.
 //
 // The un-augmented grid is > 99 % zeros, and an output pixel of a bilinear resampler is non-zero only if one of its taps
-// is.  One CTA owns one 40 x 72 output tile of one sweep and walks the sweep's 29 height channels:
-//   A  the point records of the <= 8 source row-bands under the tile's source footprint -> max into a shared-memory copy
-//      T0 of that footprint (the mirrored column of a flipped frame is already in the record)
-//   B  rotation: for every (record, one of 3 x 3 candidate destination pixels around the forward-mapped voxel) pair, in
-//      parallel over the CTA: if the pixel's cv2 fixed-point tap set really contains the voxel it is evaluated from T0
-//      with the reference's exact arithmetic (aug_geom.cuh).  Resize: the taps are separable and monotone, so an inverse
-//      tap table gives exactly the output rows / columns a source pixel feeds.  Results go into the shared output tile O;
-//      rotate + scale goes through an intermediate tile T1 (the rotated image's float32 rounding is part of the
-//      reference's result) whose non-zero pixels are listed as they are produced.
-//   C  O -> HBM (40 row pieces of 288 B, 16-byte stores; measured faster here than 40 small bulk copies), then only the
-//      touched entries of T0 / T1 are cleared again.
+// is.  The output is cut into 40 x 72 tiles; the source pixels a tile can read form its FOOTPRINT (bounding box of its
+// taps, exact, from the endpoints of cv2's monotone coordinate tables).
+//   k_rebin_aug   the row-band record bins of k_bin_fixed -> one bin per (sweep, height channel, output tile) holding the
+//                 records inside that tile's footprint (a record lands in 1-4 tiles).  One CTA per (frame, sweep,
+//                 channel) is the only writer of its 100 bins: slots come from shared-memory counters, no global atomics.
+//   k_tile_aug    one CTA per (frame, sweep, output tile) walks the sweep's 29 height channels:
+//     A  the tile's records of the channel (fetched one channel ahead with cp.async) -> max into a shared-memory copy T0
+//        of the footprint (the mirrored column of a flipped frame is already in the record)
+//     B  rotation: for every (record, one of 3 x 3 candidate destination pixels around the forward-mapped voxel) pair, in
+//        parallel over the CTA: if the pixel's cv2 fixed-point tap set really contains the voxel it is evaluated from T0
+//        with the reference's exact arithmetic (aug_geom.cuh).  Resize: the taps are separable and monotone, so an inverse
+//        tap table gives exactly the output rows / columns a source pixel feeds.  Results go into the shared output tile O;
+//        rotate + scale goes through an intermediate tile T1 (the rotated image's float32 rounding is part of the
+//        reference's result) whose non-zero pixels are listed as they are produced.
+//     C  O -> HBM (40 row pieces of 288 B, 16-byte stores; measured faster here than 40 small bulk copies), then only the
+//        touched entries of T0 / T1 are cleared again.
 // Geometry tables (warpAffine's X0/Y0/adelta/bdelta, resize taps and weights) are built once per CTA and reused for all
-// 29 channels.  Tiles whose source bands overflowed their fixed-capacity bins (dense scenes) also scan the sweep's
-// overflow list and fall back to scanning T0 for its non-zeros: slower, same bits.
+// 29 channels.  Dense scenes: a (channel, tile) bin that exceeds its capacity, or whose row bands overflowed theirs,
+// takes the SLOW path for that channel: scan the row-band bins and the sweep's overflow list, then scan T0 for its
+// non-zeros.  Slower, same bits.
 //
 // Included by lidar.cu INSIDE namespace bevgen::{anonymous}, after the tiled path's bin layout (kBinCap, kTilesPerSweep,
 // kTileElems, kFillRows, OvfRec); lidar.cu includes aug_geom.cuh at file scope first.
 #pragma once
 
-#include <type_traits>
-
 constexpr int kATW = 72, kATH = 40;                          // output tile (columns x rows): 288 B row pieces
 constexpr int kATBX = kW / kATW, kATBY = kH / kATH;          // 10 x 10 tiles per channel
+constexpr int kATTiles = kATBX * kATBY;
 constexpr int kATElems = kATW * kATH;                        // 2880 floats
 constexpr int kATThreads = 256;
-constexpr int kATMaxBands = kATThreads / 32;                 // one warp per source row-band
+constexpr int kATMaxBands = 8;                               // source row-bands under one footprint (host-checked)
+constexpr int kATCap = kATThreads;                           // records per (channel, tile) bin: one per thread
+constexpr int kBandsPerCh = kH / kFillRows;                  // 40 row-band bins per (sweep, channel)
+constexpr uint32_t kATSlow = 0xFFFFFFFFu;                    // count marking a (sweep, channel) whose row bands overflowed
 static_assert(kW % kATW == 0 && kH % kATH == 0, "tiles must cover the grid");
-static_assert((kATW * 4) % 16 == 0, "row pieces must be bulk-copy legal");
+static_assert((kATW * 4) % 16 == 0, "row pieces must be 16-byte multiples");
 
 template <bool ROT, bool SCL> struct AugTileCfg {
     // capacities (floats); the host checks a conservative bound per frame (aug_tile_supported), the kernel traps beyond
@@ -49,14 +57,14 @@ template <bool ROT, bool SCL> struct AugTileCfg {
 
 struct AugTileFrames {                                       // frames of one class, passed by value
     int n;
-    short src[60], dst[60];                                  // frame index inside the binning launch (= params index), output slot
+    // frame index inside the binning launch (= params index), output slot, slot in the per-tile bins
+    short src[60], dst[60], slot[60];
 };
 
 struct AugTileGeo {
     int dx0, dy0, DW, DH;            // rotation destination region (ROT); == the resize source region when ROT && SCL
     int qx0, qy0, QW, QH;            // resize source region (SCL)
-    int fx0, fy0, FW, FH;            // T0 footprint, clipped to the grid
-    int band0, nbands;
+    int fx0, fy0, FW, FH;            // T0 footprint, clipped to the grid (FW = 0: nothing of the tile maps into the grid)
 };
 
 struct AugTileTables {
@@ -68,11 +76,145 @@ struct AugTileTables {
     int xf[80], xl[80], yf[48], yl[48];
 };
 
-// forward (source -> destination) map of the rotation; approximate, it only places the 3 x 3 candidate window
+// forward (source -> destination) maps; approximate: they place the rotation's 3 x 3 candidate window and pick the
+// candidate output tiles of a record, the exact tests decide
 struct RotFwd { float f00, f01, f02, f10, f11, f12, hx, hy; };
+struct SclFwd { float sfx, sfy, offx, offy; };
 constexpr int kATCand = 9;                                   // rotation candidates per source voxel (3 x 3; kernel traps unless hx, hy < 1.5)
 constexpr int kATRows = 3;                                   // resize: output rows per source pixel (<= 3 for scale factors < 1.45)
 constexpr int kATOrgBias = 64;
+
+__device__ __forceinline__ RotFwd make_rot_fwd(const double* __restrict__ M) {
+    // inverse of minv (dst -> src); float is ample
+    const double a = M[0], b = M[1], c = M[2], d = M[3], e = M[4], f = M[5];
+    const double det = a * e - b * d, id = det != 0.0 ? 1.0 / det : 0.0;
+    RotFwd F;
+    F.f00 = (float)(e * id); F.f01 = (float)(-b * id); F.f10 = (float)(-d * id); F.f11 = (float)(a * id);
+    F.f02 = (float)(-(e * id * c - b * id * f)); F.f12 = (float)(-(-d * id * c + a * id * f));
+    // |dst - centre| <= |F| * 1.02 (taps within +-1 of the voxel, plus the fixed-point rounding of the coordinates)
+    F.hx = (fabsf(F.f00) + fabsf(F.f01)) * 1.03f + 0.05f;
+    F.hy = (fabsf(F.f10) + fabsf(F.f11)) * 1.03f + 0.05f;
+    return F;
+}
+__device__ __forceinline__ SclFwd make_scl_fwd(const ScalePlacement& pl) {
+    // destination x of source column u: (u + 0.5) nw/720 - 0.5 in resize coordinates, then the crop / pad shift
+    SclFwd F;
+    F.sfx = (float)pl.nw / (float)kW; F.sfy = (float)pl.nh / (float)kH;
+    F.offx = pl.crop ? -(float)pl.w0 : (float)pl.w0; F.offy = pl.crop ? -(float)pl.h0 : (float)pl.h0;
+    return F;
+}
+
+// The regions of output tile (ox0, oy0): exact, from the endpoints of cv2's monotone coordinate tables.  Both kernels
+// call this same function, so the re-binning and the tile kernel agree on every footprint.
+template <bool ROT, bool SCL>
+__device__ __forceinline__ AugTileGeo aug_tile_geo(const bevgen_aug_params& P, int ox0, int oy0) {
+    AugTileGeo G;
+    G.dx0 = ox0; G.dy0 = oy0; G.DW = kATW; G.DH = kATH;
+    G.qx0 = G.qy0 = 0; G.QW = G.QH = 0;
+    G.fx0 = G.fy0 = 0; G.FW = G.FH = 0;
+    if (SCL) {
+        const ScalePlacement pl = scale_placement(P.scale);
+        // output column ox0 + l reads resized column r = lo + l; valid while 0 <= r < nw (utils.py:464-471)
+        const int lox = pl.crop ? ox0 + pl.w0 : ox0 - pl.w0, loy = pl.crop ? oy0 + pl.h0 : oy0 - pl.h0;
+        const int c0 = max(0, -lox), c1 = min(kATW - 1, pl.nw - 1 - lox);
+        const int r0 = max(0, -loy), r1 = min(kATH - 1, pl.nh - 1 - loy);
+        if (c0 > c1 || r0 > r1) { if (ROT) { G.DW = G.DH = 0; } return G; }
+        int sa, sb, dummy;
+        float w0, w1;
+        // taps are monotone in the destination index: the region is [first s0, last s1]
+        resize_tap(lox + c0, pl.nw, kW, sa, dummy, w0, w1);
+        resize_tap(lox + c1, pl.nw, kW, dummy, sb, w0, w1);
+        G.qx0 = sa; G.QW = sb - sa + 1;
+        resize_tap(loy + r0, pl.nh, kH, sa, dummy, w0, w1);
+        resize_tap(loy + r1, pl.nh, kH, dummy, sb, w0, w1);
+        G.qy0 = sa; G.QH = sb - sa + 1;
+        if (ROT) { G.dx0 = G.qx0; G.dy0 = G.qy0; G.DW = G.QW; G.DH = G.QH; }
+        else { G.fx0 = G.qx0; G.fy0 = G.qy0; G.FW = G.QW; G.FH = G.QH; }
+    }
+    if (ROT) {
+        // X0(y) and adelta(x) are monotone: the extremes sit at the region's corners
+        const int x0a = rot_X0(P.minv, G.dy0), x0b = rot_X0(P.minv, G.dy0 + G.DH - 1);
+        const int y0a = rot_Y0(P.minv, G.dy0), y0b = rot_Y0(P.minv, G.dy0 + G.DH - 1);
+        const int aa = rot_adelta(P.minv, G.dx0), ab = rot_adelta(P.minv, G.dx0 + G.DW - 1);
+        const int ba = rot_bdelta(P.minv, G.dx0), bb = rot_bdelta(P.minv, G.dx0 + G.DW - 1);
+        const int xa = min(x0a, x0b) + min(aa, ab), xb = max(x0a, x0b) + max(aa, ab);
+        const int ya = min(y0a, y0b) + min(ba, bb), yb = max(y0a, y0b) + max(ba, bb);
+        const int fx0 = max(xa >> 10, 0), fx1 = min((xb >> 10) + 1, kW - 1);
+        const int fy0 = max(ya >> 10, 0), fy1 = min((yb >> 10) + 1, kH - 1);
+        if (fx1 >= fx0 && fy1 >= fy0) { G.fx0 = fx0; G.fy0 = fy0; G.FW = fx1 - fx0 + 1; G.FH = fy1 - fy0 + 1; }
+    }
+    return G;
+}
+
+// ---- re-binning: row-band bins -> per-(channel, output tile) bins ---------------------------------------------------
+// grid (29 channels, S sweeps, frames of the class); record = (u | v << 10, intensity bits), source pixel (u, v)
+template <bool ROT, bool SCL>
+__global__ void __launch_bounds__(kATThreads) k_rebin_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
+                                                          uint32_t* __restrict__ cnt2, uint2* __restrict__ bins2,
+                                                          const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S) {
+    __shared__ bevgen_aug_params P;
+    __shared__ int4 box[kATTiles];                           // footprint of each output tile: x0, y0, x1, y1 (inclusive)
+    __shared__ uint32_t hist[kATTiles];
+    __shared__ int s_over;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int zb = blockIdx.x, sweep = blockIdx.y;
+    const int fsrc = fl.src[blockIdx.z], slot = fl.slot[blockIdx.z];
+    {
+        const int* g = reinterpret_cast<const int*>(params + fsrc);
+        int* s = reinterpret_cast<int*>(&P);
+        for (int i = tid; i < (int)(sizeof(bevgen_aug_params) / 4); i += kATThreads) s[i] = g[i];
+    }
+    if (tid == 0) s_over = 0;
+    __syncthreads();
+    if (tid < kATTiles) {
+        const AugTileGeo G = aug_tile_geo<ROT, SCL>(P, (tid % kATBX) * kATW, (tid / kATBX) * kATH);
+        box[tid] = make_int4(G.fx0, G.fy0, G.fx0 + G.FW - 1, G.fy0 + G.FH - 1);
+        hist[tid] = 0;
+    }
+    RotFwd RF = {};
+    SclFwd SF = {};
+    if (ROT) RF = make_rot_fwd(P.minv);
+    if (SCL) SF = make_scl_fwd(scale_placement(P.scale));
+    __syncthreads();
+    const size_t bin_base = ((size_t)(fsrc * S + sweep) * kZ + zb) * kBandsPerCh;
+    uint2* const out_base = bins2 + (((size_t)(slot * S + sweep) * kZ + zb) * kATTiles) * kATCap;
+    for (int band = warp; band < kBandsPerCh; band += kATThreads / 32) {
+        uint32_t n = __ldg(cnt + bin_base + band);
+        if (n > (uint32_t)kBinCap) { if (lane == 0) s_over = 1; n = kBinCap; }
+        uint2 rec[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            rec[k] = make_uint2(0u, 0u);
+            if ((uint32_t)(lane + 32 * k) < n) rec[k] = __ldg(bins + (bin_base + band) * kBinCap + lane + 32 * k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((uint32_t)(lane + 32 * k) >= n) continue;
+            const int r = (int)(rec[k].x / (uint32_t)kW), u = (int)rec[k].x - r * kW, v = band * kFillRows + r;
+            // where the voxel lands in the output (approximately): its tile and the 8 around it are the candidates
+            float px = (float)u, py = (float)v;
+            if (ROT) { const float qx = fmaf(RF.f00, px, fmaf(RF.f01, py, RF.f02)); py = fmaf(RF.f10, px, fmaf(RF.f11, py, RF.f12)); px = qx; }
+            if (SCL) { px = (px + 0.5f) * SF.sfx - 0.5f + SF.offx; py = (py + 0.5f) * SF.sfy - 0.5f + SF.offy; }
+            const int tx = min(max((int)floorf(px * (1.0f / kATW)), 0), kATBX - 1);
+            const int ty = min(max((int)floorf(py * (1.0f / kATH)), 0), kATBY - 1);
+            const uint2 o = make_uint2((uint32_t)u | ((uint32_t)v << 10), rec[k].y);
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int cx = tx + dx, cy = ty + dy;
+                    if ((unsigned)cx >= (unsigned)kATBX || (unsigned)cy >= (unsigned)kATBY) continue;
+                    const int t = cy * kATBX + cx;
+                    const int4 b = box[t];
+                    if (u < b.x || u > b.z || v < b.y || v > b.w) continue;
+                    const uint32_t s = atomicAdd(&hist[t], 1u);
+                    if (s < (uint32_t)kATCap) out_base[(size_t)t * kATCap + s] = o;
+                }
+        }
+    }
+    __syncthreads();
+    if (tid < kATTiles) cnt2[((size_t)(slot * S + sweep) * kZ + zb) * kATTiles + tid] = s_over ? kATSlow : hist[tid];
+}
 
 // A work-list entry packs the voxel's footprint position (7 + 7 bits: the footprint is at most 127 x 127, checked) and,
 // for the rotation, the origin of its candidate window relative to the destination region (8 + 8 bits, biased).
@@ -142,8 +284,9 @@ __device__ __forceinline__ void scl_row(int u, int v, int r, const AugTileGeo& G
 template <bool ROT, bool SCL>
 __global__ void __launch_bounds__(kATThreads, AugTileCfg<ROT, SCL>::kMinBlocks)
 k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, const uint32_t* __restrict__ ovf_cnt,
-           const OvfRec* __restrict__ ovf, const int32_t* __restrict__ sweep_off, float* __restrict__ out,
-           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S) {
+           const OvfRec* __restrict__ ovf, const int32_t* __restrict__ sweep_off, const uint32_t* __restrict__ cnt2,
+           const uint2* __restrict__ bins2, float* __restrict__ out, const bevgen_aug_params* __restrict__ params,
+           AugTileFrames fl, int S) {
     static_assert(ROT || SCL, "frames that neither rotate nor scale go through k_tile_store");
     using Cfg = AugTileCfg<ROT, SCL>;
     extern __shared__ __align__(128) unsigned char at_smem[];
@@ -155,13 +298,13 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     __shared__ AugTileTables T;
     __shared__ AugTileGeo G;
     __shared__ RotFwd RF;
-    __shared__ uint32_t W[kATMaxBands * kBinCap];            // this channel's in-footprint records (at_pack_pos | rot_window_origin)
-    __shared__ uint32_t nW, nW2;
-    __shared__ uint2 Rs[kATMaxBands * kBinCap];              // staging of the NEXT channel's records (cp.async, thread-private slots)
+    __shared__ uint32_t W[kATCap];                           // this channel's records: at_pack_pos | rot_window_origin
+    __shared__ uint32_t nW2;
+    __shared__ uint2 Rs[kATCap];                             // staging of the NEXT channel's records (cp.async, thread-private slots)
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bx = blockIdx.x % kATBX, by = blockIdx.x / kATBX, sweep = blockIdx.y;
-    const int fsrc = fl.src[blockIdx.z], fdst = fl.dst[blockIdx.z];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tile = blockIdx.x, bx = tile % kATBX, by = tile / kATBX, sweep = blockIdx.y;
+    const int fsrc = fl.src[blockIdx.z], fdst = fl.dst[blockIdx.z], slot = fl.slot[blockIdx.z];
     const int ox0 = bx * kATW, oy0 = by * kATH;
     {
         const int* g = reinterpret_cast<const int*>(params + fsrc);
@@ -174,184 +317,117 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     nrect = nrect > kMaxRects ? kMaxRects : (nrect < 0 ? 0 : nrect);
 
     // ---- geometry, once per CTA ---------------------------------------------------------------------------------
-    if (SCL) {
+    if (tid == 0) {
+        G = aug_tile_geo<ROT, SCL>(P, ox0, oy0);
+        if (ROT) RF = make_rot_fwd(P.minv);
+        nW2 = 0;
+    }
+    if (SCL && tid >= 32 && tid < 32 + kATW + kATH) {
         const ScalePlacement pl = scale_placement(P.scale);
-        if (tid < kATW + kATH) {
-            const bool col = tid < kATW;
-            const int l = col ? tid : tid - kATW;
-            const int o = col ? ox0 + l : oy0 + l, off = col ? pl.w0 : pl.h0, n = col ? pl.nw : pl.nh;
-            const int r = pl.crop ? o + off : o - off;
-            int s0 = -1, s1 = -1;
-            float w0 = 0.f, w1 = 0.f;
-            if (r >= 0 && r < n) resize_tap(r, n, col ? kW : kH, s0, s1, w0, w1);
-            if (col) { T.s0x[l] = (short)s0; T.s1x[l] = (short)s1; T.wx0[l] = w0; T.wx1[l] = w1; }
-            else     { T.s0y[l] = (short)s0; T.s1y[l] = (short)s1; T.wy0[l] = w0; T.wy1[l] = w1; }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            // valid columns / rows are contiguous; taps are monotone, so the region is [first s0, last s1]
-            int c0 = 0, c1 = kATW - 1, r0 = 0, r1 = kATH - 1;
-            while (c0 <= c1 && T.s0x[c0] < 0) ++c0;
-            while (c1 >= c0 && T.s0x[c1] < 0) --c1;
-            while (r0 <= r1 && T.s0y[r0] < 0) ++r0;
-            while (r1 >= r0 && T.s0y[r1] < 0) --r1;
-            if (c0 > c1 || r0 > r1) { G.qx0 = G.qy0 = 0; G.QW = G.QH = 0; }
-            else { G.qx0 = T.s0x[c0]; G.QW = T.s1x[c1] - G.qx0 + 1; G.qy0 = T.s0y[r0]; G.QH = T.s1y[r1] - G.qy0 + 1; }
-            if (ROT) { G.dx0 = G.qx0; G.dy0 = G.qy0; G.DW = G.QW; G.DH = G.QH; }
-            else { G.fx0 = G.qx0; G.fy0 = G.qy0; G.FW = G.QW; G.FH = G.QH; }
-        }
-        __syncthreads();
-        if (G.QW > 80 || G.QH > 48) __trap();
-        // inverse tap tables: which output columns / rows of the tile read source column / row i
-        if (tid < kATW + kATH && G.QW > 0) {
-            const bool col = tid < kATW;
-            const int l = col ? tid : tid - kATW;
-            const int s0 = col ? T.s0x[l] : T.s0y[l], s1 = col ? T.s1x[l] : T.s1y[l];
-            if (s0 >= 0) {
-                int* f = col ? T.xf : T.yf;
-                int* la = col ? T.xl : T.yl;
-                const int q0 = col ? G.qx0 : G.qy0;
-                atomicMin(f + s0 - q0, l); atomicMax(la + s0 - q0, l);
-                atomicMin(f + s1 - q0, l); atomicMax(la + s1 - q0, l);
-            }
-        }
-    } else if (tid == 0) {
-        G.dx0 = ox0; G.dy0 = oy0; G.DW = kATW; G.DH = kATH;
+        const int t = tid - 32;
+        const bool col = t < kATW;
+        const int l = col ? t : t - kATW;
+        const int o = col ? ox0 + l : oy0 + l, off = col ? pl.w0 : pl.h0, n = col ? pl.nw : pl.nh;
+        const int r = pl.crop ? o + off : o - off;
+        int s0 = -1, s1 = -1;
+        float w0 = 0.f, w1 = 0.f;
+        if (r >= 0 && r < n) resize_tap(r, n, col ? kW : kH, s0, s1, w0, w1);
+        if (col) { T.s0x[l] = (short)s0; T.s1x[l] = (short)s1; T.wx0[l] = w0; T.wx1[l] = w1; }
+        else     { T.s0y[l] = (short)s0; T.s1y[l] = (short)s1; T.wy0[l] = w0; T.wy1[l] = w1; }
     }
     __syncthreads();
+    if (G.FW * G.FH > Cfg::kT0 || G.FW > 127 || G.FH > 127 || G.QW > 80 || G.QH > 48 || (ROT && (G.DW > Cfg::kDW || G.DH > Cfg::kDH)) ||
+        (ROT && SCL && G.DW * G.DH > Cfg::kT1) || (ROT && (RF.hx >= 1.5f || RF.hy >= 1.5f)))
+        __trap();
+    if (SCL && tid < kATW + kATH && G.QW > 0) {
+        // inverse tap tables: which output columns / rows of the tile read source column / row i
+        const bool col = tid < kATW;
+        const int l = col ? tid : tid - kATW;
+        const int s0 = col ? T.s0x[l] : T.s0y[l], s1 = col ? T.s1x[l] : T.s1y[l];
+        if (s0 >= 0) {
+            int* f = col ? T.xf : T.yf;
+            int* la = col ? T.xl : T.yl;
+            const int q0 = col ? G.qx0 : G.qy0;
+            atomicMin(f + s0 - q0, l); atomicMax(la + s0 - q0, l);
+            atomicMin(f + s1 - q0, l); atomicMax(la + s1 - q0, l);
+        }
+    }
     if (ROT) {
-        if (G.DW > Cfg::kDW || G.DH > Cfg::kDH) __trap();
         if (tid < G.DW) { T.A[tid] = rot_adelta(P.minv, G.dx0 + tid); T.B[tid] = rot_bdelta(P.minv, G.dx0 + tid); }
         else if (tid >= 128 && tid - 128 < G.DH) { T.X0[tid - 128] = rot_X0(P.minv, G.dy0 + tid - 128); T.Y0[tid - 128] = rot_Y0(P.minv, G.dy0 + tid - 128); }
-        if (tid == 255) {
-            // forward (src -> dst) map = inverse of minv; float is ample: it only places the candidate window
-            const double a = P.minv[0], b = P.minv[1], c = P.minv[2], d = P.minv[3], e = P.minv[4], f = P.minv[5];
-            const double det = a * e - b * d, id = det != 0.0 ? 1.0 / det : 0.0;
-            RF.f00 = (float)(e * id); RF.f01 = (float)(-b * id); RF.f10 = (float)(-d * id); RF.f11 = (float)(a * id);
-            RF.f02 = (float)(-(e * id * c - b * id * f)); RF.f12 = (float)(-(-d * id * c + a * id * f));
-            // |dst - centre| <= |F| * 1.02 (taps within +-1 of the voxel, plus the fixed-point rounding of the coordinates)
-            RF.hx = (fabsf(RF.f00) + fabsf(RF.f01)) * 1.03f + 0.05f;
-            RF.hy = (fabsf(RF.f10) + fabsf(RF.f11)) * 1.03f + 0.05f;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            if (G.DW <= 0 || G.DH <= 0) { G.fx0 = G.fy0 = 0; G.FW = G.FH = 0; }
-            else {
-                // X0(y) and adelta(x) are monotone: the extremes sit at the region's corners
-                const int xa = min(T.X0[0], T.X0[G.DH - 1]) + min(T.A[0], T.A[G.DW - 1]);
-                const int xb = max(T.X0[0], T.X0[G.DH - 1]) + max(T.A[0], T.A[G.DW - 1]);
-                const int ya = min(T.Y0[0], T.Y0[G.DH - 1]) + min(T.B[0], T.B[G.DW - 1]);
-                const int yb = max(T.Y0[0], T.Y0[G.DH - 1]) + max(T.B[0], T.B[G.DW - 1]);
-                const int fx0 = max(xa >> 10, 0), fx1 = min((xb >> 10) + 1, kW - 1);
-                const int fy0 = max(ya >> 10, 0), fy1 = min((yb >> 10) + 1, kH - 1);
-                if (fx1 < fx0 || fy1 < fy0) { G.fx0 = G.fy0 = 0; G.FW = G.FH = 0; }
-                else { G.fx0 = fx0; G.fy0 = fy0; G.FW = fx1 - fx0 + 1; G.FH = fy1 - fy0 + 1; }
-            }
-        }
-        __syncthreads();
     }
-    if (tid == 0) {
-        G.band0 = G.fy0 / kFillRows;
-        G.nbands = (G.FW > 0 && G.FH > 0) ? (G.fy0 + G.FH - 1) / kFillRows - G.band0 + 1 : 0;
-        nW = 0; nW2 = 0;
-    }
+    for (int i = tid; i < (kATElems + Cfg::kT0 + Cfg::kT1) / 4; i += kATThreads) reinterpret_cast<float4*>(at_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    const int FW = G.FW, FH = G.FH, fx0 = G.fx0, fy0 = G.fy0;
-    if (FW * FH > Cfg::kT0 || FW > 127 || FH > 127 || G.nbands > kATMaxBands || (ROT && SCL && G.DW * G.DH > Cfg::kT1)) __trap();
-    if (ROT && (RF.hx >= 1.5f || RF.hy >= 1.5f)) __trap();
     if (SCL && tid < G.QW && T.xl[tid] - T.xf[tid] >= 8) __trap();           // (never for scale factors anywhere near 1)
     if (SCL && tid < G.QH && T.yl[tid] - T.yf[tid] >= kATRows) __trap();
-    for (int i = tid; i < (kATElems + Cfg::kT0 + Cfg::kT1) / 4; i += kATThreads) reinterpret_cast<float4*>(at_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int FW = G.FW, FH = G.FH, fx0 = G.fx0, fy0 = G.fy0;
 
-    // ---- per-band record counts of all 29 channels: lane z of warp w holds cnt[z][band0 + w] ---------------------
-    const int bs = fsrc * S + sweep;
-    const int band = G.band0 + warp;
-    const bool has_band = warp < G.nbands;
+    // ---- this tile's record counts of all 29 channels: lane z holds cnt2[z][tile] (every warp the same copy) -----------
+    const size_t bin2_0 = ((size_t)(slot * S + sweep) * kZ) * kATTiles + tile;
     uint32_t c_reg = 0;
-    if (has_band && lane < kZ) c_reg = __ldg(cnt + (size_t)bs * kTilesPerSweep + lane * (kH / kFillRows) + band);
-    constexpr int kBinStrideZ = (kH / kFillRows) * kBinCap;  // records between consecutive channels of one band
-
-    // records of channel z, this warp's band: <= 4 per lane, fetched one channel ahead straight into shared memory
-    // (cp.async: no registers held across the stages, nothing waits on the load until the next channel starts);
-    // each thread reads back only the slots it filled itself, so its own wait_group is all the ordering needed
-    uint2* const rs = Rs + warp * kBinCap + lane;
-    const uint2* binp = bins + ((size_t)bs * kTilesPerSweep + band) * kBinCap + lane;
-    auto load_records = [&](int z, uint32_t& n, bool& over) {
-        const uint32_t n_all = __shfl_sync(0xFFFFFFFFu, c_reg, z);
-        over = n_all > (uint32_t)kBinCap;
-        n = over ? (uint32_t)kBinCap : n_all;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if ((uint32_t)(lane + 32 * k) < n) cp_async_8(rs + 32 * k, binp + 32 * k);
+    if (lane < kZ) c_reg = __ldg(cnt2 + bin2_0 + (size_t)lane * kATTiles);
+    // records of channel z: one per thread, fetched one channel ahead straight into shared memory (cp.async: no
+    // registers held across the stages); each thread reads back only the slot it filled itself, so its own wait_group is
+    // all the ordering needed
+    const uint2* binp = bins2 + bin2_0 * kATCap + tid;
+    auto load_records = [&](int z) -> uint32_t {
+        const uint32_t n = __shfl_sync(0xFFFFFFFFu, c_reg, z);
+        if ((uint32_t)tid < n && n <= (uint32_t)kATCap) cp_async_8(Rs + tid, binp);
         cp_async_commit();
-        binp += kBinStrideZ;
+        binp += (size_t)kATTiles * kATCap;
+        return n;
     };
-    uint32_t n = 0;
-    bool over = false;
-    load_records(0, n, over);
-    // this thread's float4s of the output tile: piece j = tid + 256 j (< 720): row j / 18, 16-byte column j % 18
-    constexpr int kPieces = (kATElems / 4 + kATThreads - 1) / kATThreads;        // 3
-    uint32_t goff[kPieces];
-#pragma unroll
-    for (int j = 0; j < kPieces; ++j) {
-        const int i = tid + j * kATThreads, r = i / (kATW / 4);
-        goff[j] = (uint32_t)(r * kW + (i - r * (kATW / 4)) * 4);
-    }
+    uint32_t n = load_records(0);
+    const int bs = fsrc * S + sweep;
     float* oplane = out + ((size_t)(fdst * S + sweep) * kZ) * kPlane + (size_t)oy0 * kW + ox0;
-    __syncthreads();
 
 #pragma unroll 1
     for (int z = 0; z < kZ; ++z, oplane += kPlane) {
-        // ---- A: records -> T0 (max), in-footprint records -> work list W (one shared atomic per warp) ----------------
+        const bool slow = n > (uint32_t)kATCap;              // uniform: over-full bin, or the channel's row bands overflowed
+        const uint32_t nw = slow ? 0u : n;
+        // ---- A: records -> T0 (max) and the work list W --------------------------------------------------------------
         cp_async_wait_all();
-        if (n) {                                             // warp-uniform
-            uint32_t word[4], m[4], total = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                word[k] = 0xFFFFFFFFu;
-                if ((uint32_t)(lane + 32 * k) < n) {
-                    const uint2 rec = rs[32 * k];
-                    const int r = (int)(rec.x / (uint32_t)kW), col = (int)rec.x - r * kW;
-                    const int fx = col - fx0, fy = band * kFillRows + r - fy0;
-                    if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH) {
+        if ((uint32_t)tid < nw) {
+            const uint2 rec = Rs[tid];
+            const int fx = (int)(rec.x & 1023u) - fx0, fy = (int)(rec.x >> 10) - fy0;       // inside the footprint by construction
+            atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, rec.y);
+            uint32_t w = at_pack_pos(fx, fy);
+            if (ROT) w |= rot_window_origin(fx0 + fx, fy0 + fy, RF, G);
+            W[tid] = w;
+        }
+        if (slow && FW > 0) {
+            // dense scene: the row-band bins under the footprint (+ the sweep's overflow list when one of them spilled)
+            bool spilled = false;
+            const int band0 = fy0 / kFillRows, band1 = (fy0 + FH - 1) / kFillRows;
+            for (int band = band0; band <= band1; ++band) {
+                const size_t t = ((size_t)bs * kZ + z) * kBandsPerCh + band;
+                uint32_t nb = __ldg(cnt + t);
+                if (nb > (uint32_t)kBinCap) { spilled = true; nb = kBinCap; }
+                if ((uint32_t)tid < nb) {
+                    const uint2 rec = __ldg(bins + t * kBinCap + tid);
+                    const int r = (int)(rec.x / (uint32_t)kW), fx = (int)rec.x - r * kW - fx0, fy = band * kFillRows + r - fy0;
+                    if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH)
                         atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, rec.y);
-                        word[k] = at_pack_pos(fx, fy);
-                        if (ROT) word[k] |= rot_window_origin(fx0 + fx, fy0 + fy, RF, G);
-                    }
                 }
-                m[k] = __ballot_sync(0xFFFFFFFFu, word[k] != 0xFFFFFFFFu);
-                total += (uint32_t)__popc(m[k]);
             }
-            if (total) {                                     // one shared atomic per warp claims the slots of all its records
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&nW, total);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (word[k] != 0xFFFFFFFFu) W[base + __popc(m[k] & ((1u << lane) - 1u))] = word[k];
-                    base += (uint32_t)__popc(m[k]);
+            if (spilled) {
+                const uint32_t n_ovf = ovf_cnt[bs];
+                const OvfRec* list = ovf + (sweep_off[bs] - sweep_off[0]);
+                for (uint32_t i = tid; i < n_ovf; i += kATThreads) {
+                    const OvfRec r = list[i];
+                    const uint32_t t = (uint32_t)(r.idx / kTileElems), cell = (uint32_t)(r.idx - (unsigned long long)t * kTileElems);
+                    const uint32_t bin_id = t - (uint32_t)bs * kTilesPerSweep;
+                    if ((int)(bin_id / kBandsPerCh) != z) continue;
+                    const int rr = (int)(cell / (uint32_t)kW), fx = (int)cell - rr * kW - fx0;
+                    const int fy = (int)(bin_id % kBandsPerCh) * kFillRows + rr - fy0;
+                    if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH)
+                        atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, r.bits);
                 }
             }
         }
-        const bool slow = __syncthreads_or(over) != 0;      // uniform: some source band of this channel overflowed its bin
-        if (z + 1 < kZ) load_records(z + 1, n, over);         // next channel's records: latency hidden behind B and C
-        if (slow) {
-            const uint32_t n_ovf = ovf_cnt[bs];
-            const OvfRec* list = ovf + (sweep_off[bs] - sweep_off[0]);
-            for (uint32_t i = tid; i < n_ovf; i += kATThreads) {
-                const OvfRec r = list[i];
-                const uint32_t tile = (uint32_t)(r.idx / kTileElems), cell = (uint32_t)(r.idx - (unsigned long long)tile * kTileElems);
-                const uint32_t bin_id = tile - (uint32_t)bs * kTilesPerSweep;
-                if ((int)(bin_id / (kH / kFillRows)) != z) continue;
-                const int rr = (int)(cell / (uint32_t)kW), col = (int)cell - rr * kW;
-                const int fx = col - fx0, fy = (int)(bin_id % (kH / kFillRows)) * kFillRows + rr - fy0;
-                if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH)
-                    atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, r.bits);
-            }
-            __syncthreads();
-        }
+        __syncthreads();
+        if (z + 1 < kZ) n = load_records(z + 1);              // next channel's records: latency hidden behind B and C
         // ---- B: every non-zero source voxel -> the destination pixels it feeds -----------------------------------------
-        const uint32_t nw = nW;
         if (ROT) {
             float* const D = SCL ? T1 : O;
             if (!slow) {
@@ -391,23 +467,21 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         }
         __syncthreads();
         // ---- C: O -> HBM (each thread re-zeroes the float4s it has just read), clear the touched entries of T0 / T1 ------
-#pragma unroll
-        for (int j = 0; j < kPieces; ++j) {
-            const int i = tid + j * kATThreads;
-            if (i < kATElems / 4) {
-                const float4 val = reinterpret_cast<const float4*>(O)[i];
-                reinterpret_cast<float4*>(O)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                __stcs(reinterpret_cast<float4*>(oplane + goff[j]), val);
-            }
+        for (int i = tid; i < kATElems / 4; i += kATThreads) {
+            const int r = i / (kATW / 4);
+            const float4 val = reinterpret_cast<const float4*>(O)[i];
+            reinterpret_cast<float4*>(O)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __stcs(reinterpret_cast<float4*>(oplane + r * kW) + (i - r * (kATW / 4)), val);
         }
         if (!slow) {
-            for (uint32_t i = tid; i < nw; i += kATThreads) { const uint32_t w = W[i]; T0[at_pos_y(w) * FW + at_pos_x(w)] = 0.f; }
-            if (ROT && SCL)
-                for (uint32_t i = tid; i < nw2; i += kATThreads) T1[W2[i]] = 0.f;
+            if ((uint32_t)tid < nw) { const uint32_t w = W[tid]; T0[at_pos_y(w) * FW + at_pos_x(w)] = 0.f; }
         } else {
-            for (int i = tid; i < (Cfg::kT0 + Cfg::kT1) / 4; i += kATThreads) reinterpret_cast<float4*>(T0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < Cfg::kT0 / 4; i += kATThreads) reinterpret_cast<float4*>(T0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (tid == 0) { nW = 0; nW2 = 0; }                   // every thread took its copies (nw, nw2) before the barrier above
+        if (ROT && SCL) {
+            for (uint32_t i = tid; i < nw2; i += kATThreads) T1[W2[i]] = 0.f;
+            if (tid == 0) nW2 = 0;                           // every thread took its copy (nw2) before the barrier above
+        }
         __syncthreads();
     }
 }
@@ -420,20 +494,23 @@ inline bool aug_tile_supported(const bevgen_aug_params& p) {
     auto bands_ok = [](int fh) { return (fh + kFillRows - 2) / kFillRows + 1 <= kATMaxBands; };   // fh rows span at most this many bands
     double dw = kATW, dh = kATH;
     if (scl) {
-        if (!(p.scale > 0.25 && p.scale < 4.0)) return false;
+        if (!(p.scale > 0.8 && p.scale < 1.25)) return false;
         const double sf = (double)(int)(kW * p.scale) / kW, sg = (double)(int)(kH * p.scale) / kH;
         if (!(sf > 0.0 && sg > 0.0)) return false;
         dw = kATW / sf + 3.0; dh = kATH / sg + 3.0;                       // resize source region of one tile
         const int qw = (int)dw + 1, qh = (int)dh + 1;
-        if (!rot) return qw * qh <= AugTileCfg<false, true>::kT0 && bands_ok(qh);
+        if (!rot) return qw * qh <= AugTileCfg<false, true>::kT0 && qw <= 80 && qh <= 48 && bands_ok(qh);
         if (qw > AugTileCfg<true, true>::kDW || qh > AugTileCfg<true, true>::kDH || qw * qh > AugTileCfg<true, true>::kT1) return false;
     }
     for (int k = 0; k < 6; ++k) if (!(p.minv[k] == p.minv[k]) || fabs(p.minv[k]) > 1e6) return false;
     const double det = p.minv[0] * p.minv[4] - p.minv[1] * p.minv[3];
-    if (!(fabs(det) > 0.25 && fabs(det) < 4.0)) return false;
+    if (!(fabs(det) > 0.8 && fabs(det) < 1.25)) return false;
+    // a record's candidate output tiles are the 3 x 3 around the tile it maps into: the footprint's bounding-box slack
+    // (region extent x |sin|) must stay well below one tile
+    if (fabs(p.minv[1]) > 0.35 || fabs(p.minv[3]) > 0.35) return false;
     // source footprint of the rotation's destination region (+2 for the taps, +2 slack for the fixed-point rounding)
     const int fw = (int)(fabs(p.minv[0]) * (dw - 1) + fabs(p.minv[1]) * (dh - 1) + 4.0) + 1;
     const int fh = (int)(fabs(p.minv[3]) * (dw - 1) + fabs(p.minv[4]) * (dh - 1) + 4.0) + 1;
-    return fw * fh <= (scl ? AugTileCfg<true, true>::kT0 : AugTileCfg<true, false>::kT0) && bands_ok(fh);
+    return fw * fh <= (scl ? AugTileCfg<true, true>::kT0 : AugTileCfg<true, false>::kT0) && fw <= 127 && fh <= 127 && bands_ok(fh);
 }
 
