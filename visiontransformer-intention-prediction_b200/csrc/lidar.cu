@@ -397,9 +397,9 @@ TiledWorkspace tiled_layout(long long total_points, int B, int S, int n_resample
     w.cnt = off;  off += align_up((ntiles + (size_t)B * S + 64) * 4, 256);      // per-tile counts, then per-sweep overflow counts
     w.bins = off; off += align_up(ntiles * kBinCap * sizeof(uint2), 256);
     w.ovf = off;  off += align_up((size_t)total_points * sizeof(OvfRec), 256);
-    const size_t nbins2 = (size_t)n_resampled * S * kZ * 100;
+    const size_t nbins2 = (size_t)n_resampled * S * kZ * kATTiles;
     w.cnt2 = off;  off += align_up(nbins2 * 4, 256);
-    w.bins2 = off; off += align_up(nbins2 * 256 * sizeof(uint2), 256);
+    w.bins2 = off; off += align_up(nbins2 * kATCap * sizeof(uint2), 256);
     w.bytes = off;
     return w;
 }
@@ -480,7 +480,6 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
         if (!aug_tile_supported(params_host[b])) return BEVGEN_E_UNSUPPORTED;
         n_resampled += (params_host[b].do_rotate != 0 || params_host[b].do_scale != 0) ? 1 : 0;
     }
-    static_assert(kATTiles == 100 && kATCap == 256, "tiled_layout sizes the per-tile bins");
     const TiledWorkspace L = tiled_layout(total_points, B, S, n_resampled);
     if (!workspace || workspace_bytes < L.bytes) return BEVGEN_E_WORKSPACE;
     char* wp = static_cast<char*>(workspace);
@@ -532,17 +531,17 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
             const dim3 rgrid(kZ, S, fl.n), grid(kATTiles, S, fl.n);
             switch (cls) {
                 case 1:
-                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, false><<<rgrid, kATThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
+                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, false><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, false><<<grid, kATThreads, AugTileCfg<true, false>::kSmem, st>>>(
                                       cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
                     break;
                 case 2:
-                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<false, true><<<rgrid, kATThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
+                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<false, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<false, true><<<grid, kATThreads, AugTileCfg<false, true>::kSmem, st>>>(
                                       cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
                     break;
                 default:
-                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, true><<<rgrid, kATThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
+                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, true><<<grid, kATThreads, AugTileCfg<true, true>::kSmem, st>>>(
                                       cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
                     break;

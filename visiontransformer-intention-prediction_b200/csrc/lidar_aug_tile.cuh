@@ -33,26 +33,35 @@
 // kTileElems, kFillRows, OvfRec); lidar.cu includes aug_geom.cuh at file scope first.
 #pragma once
 
-constexpr int kATW = 72, kATH = 40;                          // output tile (columns x rows): 288 B row pieces
+// Tile shape: 40 rows x 256 threads (4 CTAs / SM) measured against 20 rows x 128 threads (8 CTAs / SM) on B200, us per
+// 290-channel frame: rotate 90 vs 98, scale 76 vs 73, rotate+scale 175 vs 187, re-binning 10 vs 13-16.
+#ifndef BEVGEN_AT_H
+#define BEVGEN_AT_H 40
+#define BEVGEN_AT_THREADS 256
+#endif
+constexpr int kATW = 72, kATH = BEVGEN_AT_H;                 // output tile (columns x rows): 288 B row pieces
 constexpr int kATBX = kW / kATW, kATBY = kH / kATH;          // 10 x 10 tiles per channel
 constexpr int kATTiles = kATBX * kATBY;
 constexpr int kATElems = kATW * kATH;                        // 2880 floats
-constexpr int kATThreads = 256;
+constexpr int kATThreads = BEVGEN_AT_THREADS;
+constexpr int kRebinThreads = 256;
 constexpr int kATMaxBands = 8;                               // source row-bands under one footprint (host-checked)
 constexpr int kATCap = kATThreads;                           // records per (channel, tile) bin: one per thread
 constexpr int kBandsPerCh = kH / kFillRows;                  // 40 row-band bins per (sweep, channel)
 constexpr uint32_t kATSlow = 0xFFFFFFFFu;                    // count marking a (sweep, channel) whose row bands overflowed
 static_assert(kW % kATW == 0 && kH % kATH == 0, "tiles must cover the grid");
+static_assert(kATThreads >= kBinCap, "the slow path reads one row-band record per thread");
 static_assert((kATW * 4) % 16 == 0, "row pieces must be 16-byte multiples");
 
 template <bool ROT, bool SCL> struct AugTileCfg {
     // capacities (floats); the host checks a conservative bound per frame (aug_tile_supported), the kernel traps beyond
-    static constexpr int kT0 = ROT ? (SCL ? 6400 : 5120) : 3840;   // source footprint
-    static constexpr int kT1 = (ROT && SCL) ? 3840 : 0;            // rotated intermediate (= the resize's source region)
     static constexpr int kDW = SCL ? 80 : kATW;                    // rotation destination region (columns, rows)
-    static constexpr int kDH = SCL ? 48 : kATH;
+    static constexpr int kDH = SCL ? (kATH == 40 ? 48 : 26) : kATH;
+    // source footprint / rotated intermediate (= the resize's source region)
+    static constexpr int kT0 = kATH == 40 ? (ROT ? (SCL ? 6400 : 5120) : 3840) : (ROT ? (SCL ? 4096 : 3584) : 2080);
+    static constexpr int kT1 = (ROT && SCL) ? kDW * kDH : 0;
     static constexpr int kSmem = (kATElems + kT0 + kT1) * 4 + kT1 * 2;   // O, T0, T1, list of T1's non-zeros (u16)
-    static constexpr int kMinBlocks = (ROT && SCL) ? 3 : 4;
+    static constexpr int kMinBlocks = kATThreads == 256 ? ((ROT && SCL) ? 3 : 4) : ((ROT && SCL) ? 6 : 8);
 };
 
 struct AugTileFrames {                                       // frames of one class, passed by value
@@ -149,7 +158,7 @@ __device__ __forceinline__ AugTileGeo aug_tile_geo(const bevgen_aug_params& P, i
 // ---- re-binning: row-band bins -> per-(channel, output tile) bins ---------------------------------------------------
 // grid (29 channels, S sweeps, frames of the class); record = (u | v << 10, intensity bits), source pixel (u, v)
 template <bool ROT, bool SCL>
-__global__ void __launch_bounds__(kATThreads) k_rebin_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
+__global__ void __launch_bounds__(kRebinThreads) k_rebin_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
                                                           uint32_t* __restrict__ cnt2, uint2* __restrict__ bins2,
                                                           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S) {
     __shared__ bevgen_aug_params P;
@@ -162,15 +171,16 @@ __global__ void __launch_bounds__(kATThreads) k_rebin_aug(const uint32_t* __rest
     {
         const int* g = reinterpret_cast<const int*>(params + fsrc);
         int* s = reinterpret_cast<int*>(&P);
-        for (int i = tid; i < (int)(sizeof(bevgen_aug_params) / 4); i += kATThreads) s[i] = g[i];
+        for (int i = tid; i < (int)(sizeof(bevgen_aug_params) / 4); i += kRebinThreads) s[i] = g[i];
     }
     if (tid == 0) s_over = 0;
     __syncthreads();
-    if (tid < kATTiles) {
-        const AugTileGeo G = aug_tile_geo<ROT, SCL>(P, (tid % kATBX) * kATW, (tid / kATBX) * kATH);
-        box[tid] = make_int4(G.fx0, G.fy0, G.fx0 + G.FW - 1, G.fy0 + G.FH - 1);
-        hist[tid] = 0;
+    for (int t = tid; t < kATTiles; t += kRebinThreads) {
+        const AugTileGeo G = aug_tile_geo<ROT, SCL>(P, (t % kATBX) * kATW, (t / kATBX) * kATH);
+        box[t] = make_int4(G.fx0, G.fy0, G.fx0 + G.FW - 1, G.fy0 + G.FH - 1);
+        hist[t] = 0;
     }
+    constexpr int kCandY = (36 + kATH - 1) / kATH;           // 1 tile row either side at 40-row tiles, 2 at 20-row tiles
     RotFwd RF = {};
     SclFwd SF = {};
     if (ROT) RF = make_rot_fwd(P.minv);
@@ -178,42 +188,54 @@ __global__ void __launch_bounds__(kATThreads) k_rebin_aug(const uint32_t* __rest
     __syncthreads();
     const size_t bin_base = ((size_t)(fsrc * S + sweep) * kZ + zb) * kBandsPerCh;
     uint2* const out_base = bins2 + (((size_t)(slot * S + sweep) * kZ + zb) * kATTiles) * kATCap;
-    for (int band = warp; band < kBandsPerCh; band += kATThreads / 32) {
-        uint32_t n = __ldg(cnt + bin_base + band);
-        if (n > (uint32_t)kBinCap) { if (lane == 0) s_over = 1; n = kBinCap; }
-        uint2 rec[4];
+    // a warp owns the row bands warp, warp + 8, ...: all their counts, then all their records, are requested before the
+    // first one is used (the kernel is one wave of latency-bound CTAs)
+    constexpr int kWarps = kRebinThreads / 32, kPerWarp = (kBandsPerCh + kWarps - 1) / kWarps;   // 5
+    uint32_t nb[kPerWarp];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            rec[k] = make_uint2(0u, 0u);
-            if ((uint32_t)(lane + 32 * k) < n) rec[k] = __ldg(bins + (bin_base + band) * kBinCap + lane + 32 * k);
-        }
+    for (int j = 0; j < kPerWarp; ++j) {
+        const int band = warp + j * kWarps;
+        nb[j] = band < kBandsPerCh ? __ldg(cnt + bin_base + band) : 0u;
+    }
+    uint2 first[kPerWarp];                                   // records lane (< 32) of each band: most bands hold fewer than 64
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if ((uint32_t)(lane + 32 * k) >= n) continue;
-            const int r = (int)(rec[k].x / (uint32_t)kW), u = (int)rec[k].x - r * kW, v = band * kFillRows + r;
-            // where the voxel lands in the output (approximately): its tile and the 8 around it are the candidates
-            float px = (float)u, py = (float)v;
-            if (ROT) { const float qx = fmaf(RF.f00, px, fmaf(RF.f01, py, RF.f02)); py = fmaf(RF.f10, px, fmaf(RF.f11, py, RF.f12)); px = qx; }
-            if (SCL) { px = (px + 0.5f) * SF.sfx - 0.5f + SF.offx; py = (py + 0.5f) * SF.sfy - 0.5f + SF.offy; }
-            const int tx = min(max((int)floorf(px * (1.0f / kATW)), 0), kATBX - 1);
-            const int ty = min(max((int)floorf(py * (1.0f / kATH)), 0), kATBY - 1);
-            const uint2 o = make_uint2((uint32_t)u | ((uint32_t)v << 10), rec[k].y);
+    for (int j = 0; j < kPerWarp; ++j) {
+        if (nb[j] > (uint32_t)kBinCap) { if (lane == 0) s_over = 1; nb[j] = kBinCap; }
+        first[j] = make_uint2(0u, 0u);
+        if ((uint32_t)lane < nb[j]) first[j] = __ldg(bins + (bin_base + warp + j * kWarps) * kBinCap + lane);
+    }
+    auto place = [&](int band, uint2 rec) {
+        const int r = (int)(rec.x / (uint32_t)kW), u = (int)rec.x - r * kW, v = band * kFillRows + r;
+        // where the voxel lands in the output (approximately): its tile and the ones around it (a footprint's
+        // bounding box reaches < 36 rows / columns beyond the tile's own image, host-checked) are the candidates
+        float px = (float)u, py = (float)v;
+        if (ROT) { const float qx = fmaf(RF.f00, px, fmaf(RF.f01, py, RF.f02)); py = fmaf(RF.f10, px, fmaf(RF.f11, py, RF.f12)); px = qx; }
+        if (SCL) { px = (px + 0.5f) * SF.sfx - 0.5f + SF.offx; py = (py + 0.5f) * SF.sfy - 0.5f + SF.offy; }
+        const int tx = min(max((int)floorf(px * (1.0f / kATW)), 0), kATBX - 1);
+        const int ty = min(max((int)floorf(py * (1.0f / kATH)), 0), kATBY - 1);
+        const uint2 o = make_uint2((uint32_t)u | ((uint32_t)v << 10), rec.y);
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
+        for (int dy = -kCandY; dy <= kCandY; ++dy)
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int cx = tx + dx, cy = ty + dy;
-                    if ((unsigned)cx >= (unsigned)kATBX || (unsigned)cy >= (unsigned)kATBY) continue;
-                    const int t = cy * kATBX + cx;
-                    const int4 b = box[t];
-                    if (u < b.x || u > b.z || v < b.y || v > b.w) continue;
-                    const uint32_t s = atomicAdd(&hist[t], 1u);
-                    if (s < (uint32_t)kATCap) out_base[(size_t)t * kATCap + s] = o;
-                }
-        }
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int cx = tx + dx, cy = ty + dy;
+                if ((unsigned)cx >= (unsigned)kATBX || (unsigned)cy >= (unsigned)kATBY) continue;
+                const int t = cy * kATBX + cx;
+                const int4 b = box[t];
+                if (u < b.x || u > b.z || v < b.y || v > b.w) continue;
+                const uint32_t s = atomicAdd(&hist[t], 1u);
+                if (s < (uint32_t)kATCap) out_base[(size_t)t * kATCap + s] = o;
+            }
+    };
+#pragma unroll
+    for (int j = 0; j < kPerWarp; ++j) {
+        const int band = warp + j * kWarps;
+        if ((uint32_t)lane < nb[j]) place(band, first[j]);
+        for (uint32_t i = lane + 32; i < nb[j]; i += 32) place(band, __ldg(bins + (bin_base + band) * kBinCap + i));
     }
     __syncthreads();
-    if (tid < kATTiles) cnt2[((size_t)(slot * S + sweep) * kZ + zb) * kATTiles + tid] = s_over ? kATSlow : hist[tid];
+    for (int t = tid; t < kATTiles; t += kRebinThreads)
+        cnt2[((size_t)(slot * S + sweep) * kZ + zb) * kATTiles + t] = s_over ? kATSlow : hist[t];
 }
 
 // A work-list entry packs the voxel's footprint position (7 + 7 bits: the footprint is at most 127 x 127, checked) and,
@@ -312,6 +334,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         for (int i = tid; i < (int)(sizeof(bevgen_aug_params) / 4); i += kATThreads) s[i] = g[i];
     }
     if (SCL && tid < 80) { T.xf[tid] = 127; T.xl[tid] = -1; if (tid < 48) { T.yf[tid] = 127; T.yl[tid] = -1; } }
+    static_assert(kATThreads >= kATW + kATH + 32 && kATThreads >= 80, "one thread per table entry");
     __syncthreads();
     int nrect = P.n_rects;
     nrect = nrect > kMaxRects ? kMaxRects : (nrect < 0 ? 0 : nrect);
@@ -354,7 +377,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     }
     if (ROT) {
         if (tid < G.DW) { T.A[tid] = rot_adelta(P.minv, G.dx0 + tid); T.B[tid] = rot_bdelta(P.minv, G.dx0 + tid); }
-        else if (tid >= 128 && tid - 128 < G.DH) { T.X0[tid - 128] = rot_X0(P.minv, G.dy0 + tid - 128); T.Y0[tid - 128] = rot_Y0(P.minv, G.dy0 + tid - 128); }
+        else if (tid >= 80 && tid - 80 < G.DH) { T.X0[tid - 80] = rot_X0(P.minv, G.dy0 + tid - 80); T.Y0[tid - 80] = rot_Y0(P.minv, G.dy0 + tid - 80); }
     }
     for (int i = tid; i < (kATElems + Cfg::kT0 + Cfg::kT1) / 4; i += kATThreads) reinterpret_cast<float4*>(at_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
@@ -505,9 +528,9 @@ inline bool aug_tile_supported(const bevgen_aug_params& p) {
     for (int k = 0; k < 6; ++k) if (!(p.minv[k] == p.minv[k]) || fabs(p.minv[k]) > 1e6) return false;
     const double det = p.minv[0] * p.minv[4] - p.minv[1] * p.minv[3];
     if (!(fabs(det) > 0.8 && fabs(det) < 1.25)) return false;
-    // a record's candidate output tiles are the 3 x 3 around the tile it maps into: the footprint's bounding-box slack
-    // (region extent x |sin|) must stay well below one tile
-    if (fabs(p.minv[1]) > 0.35 || fabs(p.minv[3]) > 0.35) return false;
+    // a record's candidate output tiles are those within 36 rows / columns of where it maps: the footprint's
+    // bounding-box slack (region extent x |sin| + taps) must stay below that
+    if (fabs(p.minv[1]) * (dw > dh ? dw : dh) + 4.0 > 36.0 || fabs(p.minv[3]) * (dw > dh ? dw : dh) + 4.0 > 36.0) return false;
     // source footprint of the rotation's destination region (+2 for the taps, +2 slack for the fixed-point rounding)
     const int fw = (int)(fabs(p.minv[0]) * (dw - 1) + fabs(p.minv[1]) * (dh - 1) + 4.0) + 1;
     const int fh = (int)(fabs(p.minv[3]) * (dw - 1) + fabs(p.minv[4]) * (dh - 1) + 4.0) + 1;
