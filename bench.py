@@ -387,7 +387,7 @@ def run_ours(args) -> None:
             bytes_step = (B - n_gather) * own_bytes[dom]
         else:
             bytes_step = own_bytes.get(dom, fbytes) * B
-        launches = max(k["launches_per_step"], 1e-9)
+        per_step = max(k["launches_per_step"], 1e-9)
         achieved = bytes_step / (k["ms_per_step"] / 1e3) / 1e9
         traffic = None
         tpath = ROOT / "profiles" / "traffic.json"
@@ -397,8 +397,8 @@ def run_ours(args) -> None:
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_step / launches,
-                    "ms_per_launch": k["ms_per_step"] / launches}
+                    "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_step / per_step,
+                    "ms_per_launch": k["ms_per_step"] / per_step}
     step_gbs = fbytes * B / (total_ms_plain / K / 1e3) / 1e9
 
     e2e_value = frames_total / (e2e_ms / 1e3)

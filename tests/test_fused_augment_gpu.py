@@ -104,6 +104,20 @@ def test_dense_scene_overflowing_bins(bg, co, params):
     _check(bg, co, [f], [bg.AugParams(**params)], S=2)
 
 
+def test_overflowing_row_bands_with_sparse_tiles(bg, co):
+    """a thin dense line: the 10-row band bins overflow into the sweep's overflow list while every output tile still holds
+    few records -- the overflow records are re-binned per tile and take the fast path"""
+    import dataclasses
+    rng = np.random.default_rng(11)
+    n = 3000
+    pts = np.stack([rng.uniform(9.9, 10.3, n), rng.uniform(-72, 72, n), rng.uniform(0.0, 0.15, n),
+                    rng.integers(1, 256, n)], 1).astype(np.float32)
+    base = bg.synthetic.frame_c1(0, n=10)
+    f = dataclasses.replace(base, points4=pts, sweep_offsets=np.array([0, n], np.int64))
+    for p in (bg.AugParams(angle_deg=-11.0), bg.AugParams(scale=1.04, flip=True), bg.AugParams(scale=0.96, angle_deg=6.0)):
+        _check(bg, co, [f], [p], S=1)
+
+
 def test_grid_aligned_points_and_borders(bg, co):
     """points on voxel boundaries and along the grid borders (taps that fall outside the grid are zeros)"""
     rng = np.random.default_rng(7)

@@ -531,17 +531,17 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
             const dim3 rgrid(kZ, S, fl.n), grid(kATTiles, S, fl.n);
             switch (cls) {
                 case 1:
-                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, false><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
+                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, false><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, false><<<grid, kATThreads, AugTileCfg<true, false>::kSmem, st>>>(
                                       cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
                     break;
                 case 2:
-                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<false, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
+                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<false, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<false, true><<<grid, kATThreads, AugTileCfg<false, true>::kSmem, st>>>(
                                       cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
                     break;
                 default:
-                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, cnt2, bins2, in.aug, fl, S));
+                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, true><<<grid, kATThreads, AugTileCfg<true, true>::kSmem, st>>>(
                                       cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
                     break;

@@ -11,8 +11,9 @@
 // is.  The output is cut into 40 x 72 tiles; the source pixels a tile can read form its FOOTPRINT (bounding box of its
 // taps, exact, from the endpoints of cv2's monotone coordinate tables).
 //   k_rebin_aug   the row-band record bins of k_bin_fixed -> one bin per (sweep, height channel, output tile) holding the
-//                 records inside that tile's footprint (a record lands in 1-4 tiles).  One CTA per (frame, sweep,
-//                 channel) is the only writer of its 100 bins: slots come from shared-memory counters, no global atomics.
+//                 records inside that tile's footprint (a record lands in 1-4 tiles), including the channel's records in
+//                 the sweep's overflow list.  One CTA per (frame, sweep, channel) is the only writer of its 100 bins:
+//                 slots come from shared-memory counters, no global atomics.
 //   k_tile_aug    one CTA per (frame, sweep, output tile) walks the sweep's 29 height channels:
 //     A  the tile's records of the channel (fetched one channel ahead with cp.async) -> max into a shared-memory copy T0
 //        of the footprint (the mirrored column of a flipped frame is already in the record)
@@ -25,9 +26,8 @@
 //     C  O -> HBM (40 row pieces of 288 B, 16-byte stores; measured faster here than 40 small bulk copies), then only the
 //        touched entries of T0 / T1 are cleared again.
 // Geometry tables (warpAffine's X0/Y0/adelta/bdelta, resize taps and weights) are built once per CTA and reused for all
-// 29 channels.  Dense scenes: a (channel, tile) bin that exceeds its capacity, or whose row bands overflowed theirs,
-// takes the SLOW path for that channel: scan the row-band bins and the sweep's overflow list, then scan T0 for its
-// non-zeros.  Slower, same bits.
+// 29 channels.  Dense scenes: a (channel, tile) bin that exceeds its capacity (256 records) takes the SLOW path for that
+// channel: scan the row-band bins and the sweep's overflow list, then scan T0 for its non-zeros.  Slower, same bits.
 //
 // Included by lidar.cu INSIDE namespace bevgen::{anonymous}, after the tiled path's bin layout (kBinCap, kTilesPerSweep,
 // kTileElems, kFillRows, OvfRec); lidar.cu includes aug_geom.cuh at file scope first.
@@ -48,7 +48,6 @@ constexpr int kRebinThreads = 256;
 constexpr int kATMaxBands = 8;                               // source row-bands under one footprint (host-checked)
 constexpr int kATCap = kATThreads;                           // records per (channel, tile) bin: one per thread
 constexpr int kBandsPerCh = kH / kFillRows;                  // 40 row-band bins per (sweep, channel)
-constexpr uint32_t kATSlow = 0xFFFFFFFFu;                    // count marking a (sweep, channel) whose row bands overflowed
 static_assert(kW % kATW == 0 && kH % kATH == 0, "tiles must cover the grid");
 static_assert(kATThreads >= kBinCap, "the slow path reads one row-band record per thread");
 static_assert((kATW * 4) % 16 == 0, "row pieces must be 16-byte multiples");
@@ -159,6 +158,8 @@ __device__ __forceinline__ AugTileGeo aug_tile_geo(const bevgen_aug_params& P, i
 // grid (29 channels, S sweeps, frames of the class); record = (u | v << 10, intensity bits), source pixel (u, v)
 template <bool ROT, bool SCL>
 __global__ void __launch_bounds__(kRebinThreads) k_rebin_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
+                                                          const uint32_t* __restrict__ ovf_cnt, const OvfRec* __restrict__ ovf,
+                                                          const int32_t* __restrict__ sweep_off,
                                                           uint32_t* __restrict__ cnt2, uint2* __restrict__ bins2,
                                                           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S) {
     __shared__ bevgen_aug_params P;
@@ -234,8 +235,22 @@ __global__ void __launch_bounds__(kRebinThreads) k_rebin_aug(const uint32_t* __r
         for (uint32_t i = lane + 32; i < nb[j]; i += 32) place(band, __ldg(bins + (bin_base + band) * kBinCap + i));
     }
     __syncthreads();
+    if (s_over) {
+        // a row band of this channel spilled into the sweep's overflow list: its records of this channel are re-binned too
+        const int bs = fsrc * S + sweep;
+        const uint32_t n_ovf = ovf_cnt[bs];
+        const OvfRec* list = ovf + (sweep_off[bs] - sweep_off[0]);
+        for (uint32_t i = tid; i < n_ovf; i += kRebinThreads) {
+            const OvfRec r = list[i];
+            const uint32_t t = (uint32_t)(r.idx / kTileElems), cell = (uint32_t)(r.idx - (unsigned long long)t * kTileElems);
+            const uint32_t bin_id = t - (uint32_t)bs * kTilesPerSweep;
+            if ((int)(bin_id / kBandsPerCh) == zb) place((int)(bin_id % kBandsPerCh), make_uint2(cell, r.bits));
+        }
+        __syncthreads();
+    }
+    // a count above kATCap sends that (channel, tile) down the tile kernel's slow path
     for (int t = tid; t < kATTiles; t += kRebinThreads)
-        cnt2[((size_t)(slot * S + sweep) * kZ + zb) * kATTiles + t] = s_over ? kATSlow : hist[t];
+        cnt2[((size_t)(slot * S + sweep) * kZ + zb) * kATTiles + t] = hist[t];
 }
 
 // A work-list entry packs the voxel's footprint position (7 + 7 bits: the footprint is at most 127 x 127, checked) and,
@@ -300,6 +315,41 @@ __device__ __forceinline__ void scl_row(int u, int v, int r, const AugTileGeo& G
         if (nrect && in_rects(rects, nrect, oy0 + ly, ox0 + lx)) continue;                      // utils.py:496
         const int a0 = T.s0x[lx], a1 = T.s1x[lx];
         O[ly * kATW + lx] = resize_sum(r0[a0], r0[a1], r1[a0], r1[a1], T.wx0[lx], T.wx1[lx], wy0, wy1);
+    }
+}
+
+// Slow path, dense scenes: the row-band bins under the footprint (+ the sweep's overflow list when one of them spilled)
+// -> max into T0.  Kept out of line so that its registers do not count against the common path.
+static __device__ __noinline__ void at_slow_fill(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
+                                                 const uint32_t* __restrict__ ovf_cnt, const OvfRec* __restrict__ ovf,
+                                                 const int32_t* __restrict__ sweep_off, int bs, int z, int fx0, int fy0, int FW, int FH,
+                                                 float* __restrict__ T0) {
+    const int tid = threadIdx.x;
+    bool spilled = false;
+    const int band0 = fy0 / kFillRows, band1 = (fy0 + FH - 1) / kFillRows;
+    for (int band = band0; band <= band1; ++band) {
+        const size_t t = ((size_t)bs * kZ + z) * kBandsPerCh + band;
+        uint32_t nb = __ldg(cnt + t);
+        if (nb > (uint32_t)kBinCap) { spilled = true; nb = kBinCap; }
+        if ((uint32_t)tid < nb) {
+            const uint2 rec = __ldg(bins + t * kBinCap + tid);
+            const int r = (int)(rec.x / (uint32_t)kW), fx = (int)rec.x - r * kW - fx0, fy = band * kFillRows + r - fy0;
+            if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH)
+                atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, rec.y);
+        }
+    }
+    if (!spilled) return;
+    const uint32_t n_ovf = ovf_cnt[bs];
+    const OvfRec* list = ovf + (sweep_off[bs] - sweep_off[0]);
+    for (uint32_t i = tid; i < n_ovf; i += kATThreads) {
+        const OvfRec r = list[i];
+        const uint32_t t = (uint32_t)(r.idx / kTileElems), cell = (uint32_t)(r.idx - (unsigned long long)t * kTileElems);
+        const uint32_t bin_id = t - (uint32_t)bs * kTilesPerSweep;
+        if ((int)(bin_id / kBandsPerCh) != z) continue;
+        const int rr = (int)(cell / (uint32_t)kW), fx = (int)cell - rr * kW - fx0;
+        const int fy = (int)(bin_id % kBandsPerCh) * kFillRows + rr - fy0;
+        if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH)
+            atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, r.bits);
     }
 }
 
@@ -406,7 +456,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
 
 #pragma unroll 1
     for (int z = 0; z < kZ; ++z, oplane += kPlane) {
-        const bool slow = n > (uint32_t)kATCap;              // uniform: over-full bin, or the channel's row bands overflowed
+        const bool slow = n > (uint32_t)kATCap;              // uniform: over-full bin (dense scene)
         const uint32_t nw = slow ? 0u : n;
         // ---- A: records -> T0 (max) and the work list W --------------------------------------------------------------
         cp_async_wait_all();
@@ -418,36 +468,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
             if (ROT) w |= rot_window_origin(fx0 + fx, fy0 + fy, RF, G);
             W[tid] = w;
         }
-        if (slow && FW > 0) {
-            // dense scene: the row-band bins under the footprint (+ the sweep's overflow list when one of them spilled)
-            bool spilled = false;
-            const int band0 = fy0 / kFillRows, band1 = (fy0 + FH - 1) / kFillRows;
-            for (int band = band0; band <= band1; ++band) {
-                const size_t t = ((size_t)bs * kZ + z) * kBandsPerCh + band;
-                uint32_t nb = __ldg(cnt + t);
-                if (nb > (uint32_t)kBinCap) { spilled = true; nb = kBinCap; }
-                if ((uint32_t)tid < nb) {
-                    const uint2 rec = __ldg(bins + t * kBinCap + tid);
-                    const int r = (int)(rec.x / (uint32_t)kW), fx = (int)rec.x - r * kW - fx0, fy = band * kFillRows + r - fy0;
-                    if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH)
-                        atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, rec.y);
-                }
-            }
-            if (spilled) {
-                const uint32_t n_ovf = ovf_cnt[bs];
-                const OvfRec* list = ovf + (sweep_off[bs] - sweep_off[0]);
-                for (uint32_t i = tid; i < n_ovf; i += kATThreads) {
-                    const OvfRec r = list[i];
-                    const uint32_t t = (uint32_t)(r.idx / kTileElems), cell = (uint32_t)(r.idx - (unsigned long long)t * kTileElems);
-                    const uint32_t bin_id = t - (uint32_t)bs * kTilesPerSweep;
-                    if ((int)(bin_id / kBandsPerCh) != z) continue;
-                    const int rr = (int)(cell / (uint32_t)kW), fx = (int)cell - rr * kW - fx0;
-                    const int fy = (int)(bin_id % kBandsPerCh) * kFillRows + rr - fy0;
-                    if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH)
-                        atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, r.bits);
-                }
-            }
-        }
+        if (slow && FW > 0) at_slow_fill(cnt, bins, ovf_cnt, ovf, sweep_off, bs, z, fx0, fy0, FW, FH, T0);
         __syncthreads();
         if (z + 1 < kZ) n = load_records(z + 1);              // next channel's records: latency hidden behind B and C
         // ---- B: every non-zero source voxel -> the destination pixels it feeds -----------------------------------------
