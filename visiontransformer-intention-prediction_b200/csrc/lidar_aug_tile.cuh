@@ -320,10 +320,17 @@ __device__ __forceinline__ void scl_row(int u, int v, int r, const AugTileGeo& G
 
 // Slow path, dense scenes: the row-band bins under the footprint (+ the sweep's overflow list when one of them spilled)
 // -> max into T0.  Kept out of line so that its registers do not count against the common path.
-static __device__ __noinline__ void at_slow_fill(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
-                                                 const uint32_t* __restrict__ ovf_cnt, const OvfRec* __restrict__ ovf,
-                                                 const int32_t* __restrict__ sweep_off, int bs, int z, int fx0, int fy0, int FW, int FH,
-                                                 float* __restrict__ T0) {
+struct AugSlowArgs {                                         // parked in shared memory: only the slow path reads them
+    const uint32_t* cnt; const uint2* bins; const uint32_t* ovf_cnt; const OvfRec* ovf; const int32_t* sweep_off;
+    int bs;
+};
+static __device__ __noinline__ void at_slow_fill(const AugSlowArgs* a, int z, int fx0, int fy0, int FW, int FH, float* __restrict__ T0) {
+    const uint32_t* __restrict__ cnt = a->cnt;
+    const uint2* __restrict__ bins = a->bins;
+    const uint32_t* __restrict__ ovf_cnt = a->ovf_cnt;
+    const OvfRec* __restrict__ ovf = a->ovf;
+    const int32_t* __restrict__ sweep_off = a->sweep_off;
+    const int bs = a->bs;
     const int tid = threadIdx.x;
     bool spilled = false;
     const int band0 = fy0 / kFillRows, band1 = (fy0 + FH - 1) / kFillRows;
@@ -373,6 +380,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     __shared__ uint32_t W[kATCap];                           // this channel's records: at_pack_pos | rot_window_origin
     __shared__ uint32_t nW2;
     __shared__ uint2 Rs[kATCap];                             // staging of the NEXT channel's records (cp.async, thread-private slots)
+    __shared__ AugSlowArgs SA;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x, bx = tile % kATBX, by = tile / kATBX, sweep = blockIdx.y;
@@ -391,6 +399,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
 
     // ---- geometry, once per CTA ---------------------------------------------------------------------------------
     if (tid == 0) {
+        SA.cnt = cnt; SA.bins = bins; SA.ovf_cnt = ovf_cnt; SA.ovf = ovf; SA.sweep_off = sweep_off; SA.bs = fsrc * S + sweep;
         G = aug_tile_geo<ROT, SCL>(P, ox0, oy0);
         if (ROT) RF = make_rot_fwd(P.minv);
         nW2 = 0;
@@ -451,7 +460,6 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         return n;
     };
     uint32_t n = load_records(0);
-    const int bs = fsrc * S + sweep;
     float* oplane = out + ((size_t)(fdst * S + sweep) * kZ) * kPlane + (size_t)oy0 * kW + ox0;
 
 #pragma unroll 1
@@ -468,7 +476,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
             if (ROT) w |= rot_window_origin(fx0 + fx, fy0 + fy, RF, G);
             W[tid] = w;
         }
-        if (slow && FW > 0) at_slow_fill(cnt, bins, ovf_cnt, ovf, sweep_off, bs, z, fx0, fy0, FW, FH, T0);
+        if (slow && FW > 0) at_slow_fill(&SA, z, fx0, fy0, FW, FH, T0);
         __syncthreads();
         if (z + 1 < kZ) n = load_records(z + 1);              // next channel's records: latency hidden behind B and C
         // ---- B: every non-zero source voxel -> the destination pixels it feeds -----------------------------------------
