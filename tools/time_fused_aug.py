@@ -10,7 +10,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 only = sys.argv[2] if len(sys.argv) > 2 else None
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 kind = sys.argv[4] if len(sys.argv) > 4 else "c2"
-mk = {"c2": bg.synthetic.frame_c2, "c4": bg.synthetic.frame_c4}[kind]
+mk = {"c2": bg.synthetic.frame_c2, "c4": bg.synthetic.frame_c4, "empty": lambda i: bg.synthetic.frame_c2(i, n=1)}[kind]
 frames = [mk(i) for i in range(2)]
 frames = [frames[i % 2] for i in range(B)]
 batch = bg.FrameBatch.pack(frames, 10)

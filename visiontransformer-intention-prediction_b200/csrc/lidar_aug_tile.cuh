@@ -386,6 +386,16 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     const int tile = blockIdx.x, bx = tile % kATBX, by = tile / kATBX, sweep = blockIdx.y;
     const int fsrc = fl.src[blockIdx.z], fdst = fl.dst[blockIdx.z], slot = fl.slot[blockIdx.z];
     const int ox0 = bx * kATW, oy0 = by * kATH;
+    // everything the start-up needs from global memory is requested at once: the parameters, this tile's record counts of
+    // all 29 channels (lane z holds cnt2[z][tile]; every warp the same copy) and the first channel's whole bin (its count
+    // is not known yet; 2 KB once per CTA)
+    const size_t bin2_0 = ((size_t)(slot * S + sweep) * kZ) * kATTiles + tile;
+    uint32_t c_reg = 0;
+    if (lane < kZ) c_reg = __ldg(cnt2 + bin2_0 + (size_t)lane * kATTiles);
+    const uint2* binp = bins2 + bin2_0 * kATCap + tid;
+    cp_async_8(Rs + tid, binp);
+    cp_async_commit();
+    binp += (size_t)kATTiles * kATCap;
     {
         const int* g = reinterpret_cast<const int*>(params + fsrc);
         int* s = reinterpret_cast<int*>(&P);
@@ -401,9 +411,9 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     if (tid == 0) {
         SA.cnt = cnt; SA.bins = bins; SA.ovf_cnt = ovf_cnt; SA.ovf = ovf; SA.sweep_off = sweep_off; SA.bs = fsrc * S + sweep;
         G = aug_tile_geo<ROT, SCL>(P, ox0, oy0);
-        if (ROT) RF = make_rot_fwd(P.minv);
         nW2 = 0;
     }
+    if (ROT && tid == kATThreads - 32) RF = make_rot_fwd(P.minv);
     if (SCL && tid >= 32 && tid < 32 + kATW + kATH) {
         const ScalePlacement pl = scale_placement(P.scale);
         const int t = tid - 32;
@@ -444,14 +454,9 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     if (SCL && tid < G.QH && T.yl[tid] - T.yf[tid] >= kATRows) __trap();
     const int FW = G.FW, FH = G.FH, fx0 = G.fx0, fy0 = G.fy0;
 
-    // ---- this tile's record counts of all 29 channels: lane z holds cnt2[z][tile] (every warp the same copy) -----------
-    const size_t bin2_0 = ((size_t)(slot * S + sweep) * kZ) * kATTiles + tile;
-    uint32_t c_reg = 0;
-    if (lane < kZ) c_reg = __ldg(cnt2 + bin2_0 + (size_t)lane * kATTiles);
     // records of channel z: one per thread, fetched one channel ahead straight into shared memory (cp.async: no
     // registers held across the stages); each thread reads back only the slot it filled itself, so its own wait_group is
     // all the ordering needed
-    const uint2* binp = bins2 + bin2_0 * kATCap + tid;
     auto load_records = [&](int z) -> uint32_t {
         const uint32_t n = __shfl_sync(0xFFFFFFFFu, c_reg, z);
         if ((uint32_t)tid < n && n <= (uint32_t)kATCap) cp_async_8(Rs + tid, binp);
@@ -459,7 +464,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         binp += (size_t)kATTiles * kATCap;
         return n;
     };
-    uint32_t n = load_records(0);
+    uint32_t n = __shfl_sync(0xFFFFFFFFu, c_reg, 0);         // channel 0's records were requested at the top
     float* oplane = out + ((size_t)(fdst * S + sweep) * kZ) * kPlane + (size_t)oy0 * kW + ox0;
 
 #pragma unroll 1
