@@ -95,3 +95,42 @@ def test_no_cuda_means_loud_failure(bg):
         bg.create_intentnet_lidar_bev([np.zeros((3, 3))], [np.ones(3, np.float32)])
     with pytest.raises(RuntimeError):
         bg.transform_points(np.zeros((3, 3), np.float32), np.eye(4))
+
+
+def test_pinned_pool_never_aliases_live_results(monkeypatch):
+    """The reference-signature functions return fresh arrays (utils.py:70, :146, :182); ours are backed by pooled pinned
+    buffers that may only be recycled once the array, its views and its torch.from_numpy aliases are all gone."""
+    import gc
+    import torch
+    from bevgen_b200 import bev_ops
+    pool = bev_ops._PinnedPool()
+
+    def take(n):                                   # no CUDA here: pageable stand-ins for the pinned buffers
+        lst = pool._free.get(n)
+        if lst:
+            pool._idle_bytes -= n
+            return lst.pop()
+        return torch.empty(n, dtype=torch.uint8)
+
+    class _Stream:
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(pool, "take", take)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda: _Stream())
+    t = torch.arange(1 << 19, dtype=torch.float32)
+    a, b = pool.to_numpy(t), pool.to_numpy(t + 1)
+    assert a.ctypes.data != b.ctypes.data and a[5] == 5 and b[5] == 6      # two live results: two buffers
+    view, ptr = a[10:20], a.ctypes.data
+    del a
+    gc.collect()
+    assert pool._idle_bytes == 0                   # a view keeps the buffer out of the pool
+    alias = torch.from_numpy(view)                 # what dataset.py:355 does
+    del view
+    gc.collect()
+    assert pool._idle_bytes == 0
+    del alias
+    gc.collect()
+    assert pool._idle_bytes == t.numel() * 4       # now it is back
+    c = pool.to_numpy(t * 2)
+    assert c.ctypes.data == ptr and c[3] == 6 and b[5] == 6               # recycled; the live result is untouched

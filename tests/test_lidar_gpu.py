@@ -194,3 +194,21 @@ def test_fp16_packed_points(bg, co):
         assert np.array_equal(got, want), algo
     with pytest.raises(ValueError):
         bg.FrameBatch.pack([bg.synthetic.frame_c2(3, n=100)], 10, points_dtype=np.float16)   # not fp16-representable
+
+
+def test_reference_signature_results_are_independent_arrays(bg):
+    """create_intentnet_lidar_bev returns a new array per call (utils.py:70): results backed by pooled pinned memory must
+    not alias while alive, and must be ordinary writable numpy arrays"""
+    f = bg.synthetic.frame_c1(0, n=3_000)
+    pts = [bg.transform_points(f.sweep(0)[:, :3], f.rel_tf[0])]
+    inten = [f.sweep(0)[:, 3].copy()]
+    a = bg.create_intentnet_lidar_bev(pts, inten)
+    b = bg.create_intentnet_lidar_bev(pts, inten)
+    assert a.ctypes.data != b.ctypes.data and np.array_equal(a, b)
+    assert a.flags.writeable and a.flags.c_contiguous and a.dtype == np.float32
+    a[0, 0, 0] = 123.0
+    assert b[0, 0, 0] != 123.0
+    t = torch.from_numpy(a).float()                 # dataset.py:355: no copy for float32
+    del a
+    c = bg.create_intentnet_lidar_bev(pts, inten)
+    assert t[0, 0, 0] == 123.0 and c[0, 0, 0] != 123.0

@@ -74,23 +74,63 @@ class _Workspace:
 
 workspace = _Workspace()
 
-_pinned_stage = {}
+class _PinnedPool:
+    """Pinned host buffers handed out as the backing store of the numpy arrays the reference-signature functions return.
+
+    The reference returns a FRESH array per call (utils.py:70, :146, :182).  Allocating 334 MB of pageable memory per call
+    costs more than the whole GPU path (page faults + a pageable device->host copy), and so does a pinned staging
+    buffer plus a host memcpy.  Instead the array returned IS a pinned buffer: the device->host copy runs at full PCIe rate
+    straight into it, and the buffer goes back to the pool only when the array (and every view / ``torch.from_numpy`` alias
+    of it) has been garbage-collected -- so no two live results ever share memory, which is all "fresh" means to a caller.
+    Small results (< 1 MiB) take the plain path."""
+
+    MIN_BYTES = 1 << 20
+    MAX_IDLE_BYTES = 8 << 30          # idle buffers kept for reuse; anything above is released to the OS
+
+    def __init__(self) -> None:
+        self._free = {}               # nbytes -> [uint8 pinned tensors]
+        self._idle_bytes = 0
+
+    def _release(self, buf: torch.Tensor) -> None:
+        n = buf.numel()
+        if self._idle_bytes + n > self.MAX_IDLE_BYTES:
+            return                    # dropped: freed by torch
+        self._free.setdefault(n, []).append(buf)
+        self._idle_bytes += n
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        lst = self._free.get(nbytes)
+        if lst:
+            self._idle_bytes -= nbytes
+            return lst.pop()
+        return torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+
+    def to_numpy(self, t: torch.Tensor) -> np.ndarray:
+        import weakref
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        buf = self.take(nbytes)
+        host = buf.view(t.dtype).reshape(t.shape)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        arr = host.numpy()
+        weakref.finalize(arr, self._release, buf)     # numpy views keep `arr` alive through .base, so this fires last
+        return arr
+
+    def clear(self) -> None:
+        self._free.clear()
+        self._idle_bytes = 0
+
+
+pinned_pool = _PinnedPool()
 
 
 def to_numpy_fresh(t: torch.Tensor) -> np.ndarray:
-    """Device tensor -> NEW numpy array (what the reference's functions return).  Goes through a cached pinned staging
-    buffer: a full-rate PCIe copy plus one host memcpy, instead of a pageable device->host copy."""
-    t = t.contiguous()
-    key = (t.dtype, t.numel())
-    stage = _pinned_stage.get(key)
-    if stage is None:
-        if len(_pinned_stage) > 8:
-            _pinned_stage.clear()
-        stage = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
-        _pinned_stage[key] = stage
-    stage.copy_(t.reshape(-1), non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    return stage.numpy().reshape(tuple(t.shape)).copy()
+    """Device tensor -> NEW numpy array (what the reference's functions return); large results live in pooled pinned
+    memory (see _PinnedPool), small ones are plain copies."""
+    if t.numel() * t.element_size() < _PinnedPool.MIN_BYTES:
+        return t.cpu().numpy()
+    return pinned_pool.to_numpy(t)
 
 
 def _aug_fusion_args(B, flip, drop_rects, drop_counts, device):
