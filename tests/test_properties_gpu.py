@@ -72,3 +72,43 @@ def test_batch_equals_singles_and_shards(bg):
             sub = sharding.shard_frames(frames, r, w)
             parts.append(gen.generate(bg.FrameBatch.pack(sub, 10), with_map=False)["lidar_bev"].clone())
         assert torch.equal(torch.cat(parts), whole)
+
+
+@settings(max_examples=10, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(seed=st.integers(0, 10_000), n=st.integers(1, 4000), S=st.integers(1, 4), angle=st.one_of(st.none(), st.floats(-15, 15)),
+       scale=st.one_of(st.none(), st.floats(0.95, 1.05)), flip=st.booleans())
+def test_fused_generation_plus_augmentation_matches_oracle_and_is_order_free(bg, seed, n, S, angle, scale, flip):
+    """bevgen_lidar_bev_augmented == oracle generation followed by the oracle's flip -> rotate -> scale, for any draw in
+    the reference's parameter ranges; permuting the points of a sweep changes nothing (max is order-free)"""
+    from oracle import c_oracle as co
+    f = _frame(seed, n, S)
+    p = bg.AugParams(flip=flip, angle_deg=angle, scale=scale)
+    g = co.lidar_bev_fused(f.points4, f.sweep_offsets, f.rel_tf, S)
+    if flip: g = co.flip_w(g)
+    if angle is not None: g = co.rotate(g, angle)
+    if scale is not None: g = co.scale(g, scale)
+    dev = torch.device("cuda")
+    fb = bg.FrameBatch.pack([f], S)
+    args = (fb.sweep_offsets.to(dev), fb.rel_tf.to(dev), 1, S, [p])
+    got = bg.augment.lidar_bev_augmented(fb.points4.to(dev), *args, max_sweep_points=fb.max_sweep_points)[0]
+    assert torch.equal(got.cpu(), torch.from_numpy(np.ascontiguousarray(g)))
+    rng = np.random.default_rng(seed)
+    p2 = f.points4.copy()
+    for s in range(S):
+        a, b = f.sweep_offsets[s], f.sweep_offsets[s + 1]
+        p2[a:b] = p2[a:b][rng.permutation(b - a)]
+    again = bg.augment.lidar_bev_augmented(torch.from_numpy(p2).to(dev), *args, max_sweep_points=fb.max_sweep_points)[0]
+    assert torch.equal(got, again)
+
+
+def test_fused_equals_dense_route_at_full_size(bg):
+    """BASELINE.json's frame size (10 sweeps x 100k points): building the augmented grid from the point records gives
+    the same bits as generating the grid and resampling it (size-independent property; the oracle takes minutes here)"""
+    frames = [bg.synthetic.frame_c2(70 + i) for i in range(3)]
+    aug = [bg.AugParams(angle_deg=-13.7, flip=True), bg.AugParams(scale=1.047, rects=[(30, 600, 45, 50)]),
+           bg.AugParams(angle_deg=8.1, scale=0.953)]
+    fb = bg.FrameBatch.pack(frames, 10)
+    a = bg.BevGenerator(fused_augment=True).generate(fb, aug, with_map=False)["lidar_bev"]
+    b = bg.BevGenerator(fused_augment=False).generate(fb, aug, with_map=False)["lidar_bev"]
+    assert torch.equal(a, b)
+    assert int((a != 0).sum()) > 3_000_000
