@@ -567,6 +567,15 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
 
 using namespace bevgen;
 
+#ifdef BEVGEN_AT_PROFILE
+extern "C" int bevgen_debug_at_profile(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_at_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_at_prof, z, sizeof z); }
+    return 0;
+}
+#endif
+
 extern "C" size_t bevgen_lidar_aug_workspace_bytes(int64_t total_points, int B, int S, int n_resampled) {
     if (total_points < 0 || B <= 0 || S <= 0 || n_resampled < 0 || n_resampled > B) return 0;
     return tiled_layout(total_points, B, S, n_resampled).bytes;

@@ -360,6 +360,13 @@ static __device__ __noinline__ void at_slow_fill(const AugSlowArgs* a, int z, in
     }
 }
 
+#ifdef BEVGEN_AT_PROFILE
+__device__ unsigned long long g_at_prof[16];
+#define AT_TICK(k) do { if (tid == PROF_TID) { const long long t_ = clock64(); prof[k] += t_ - tprev; tprev = t_; } } while (0)
+#else
+#define AT_TICK(k) do {} while (0)
+#endif
+
 template <bool ROT, bool SCL>
 __global__ void __launch_bounds__(kATThreads, AugTileCfg<ROT, SCL>::kMinBlocks)
 k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, const uint32_t* __restrict__ ovf_cnt,
@@ -379,7 +386,8 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     __shared__ RotFwd RF;
     __shared__ uint32_t W[kATCap];                           // this channel's records: at_pack_pos | rot_window_origin
     __shared__ uint32_t nW2;
-    __shared__ uint2 Rs[kATCap];                             // staging of the NEXT channel's records (cp.async, thread-private slots)
+    __shared__ uint2 Rs[2][kATCap];                          // cp.async staging, thread-private slots: channel z lands in Rs[z & 1]
+    __shared__ uint32_t cN[kZ + 3];                          // this tile's record count per channel (0 past the last one)
     __shared__ AugSlowArgs SA;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -387,15 +395,15 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     const int fsrc = fl.src[blockIdx.z], fdst = fl.dst[blockIdx.z], slot = fl.slot[blockIdx.z];
     const int ox0 = bx * kATW, oy0 = by * kATH;
     // everything the start-up needs from global memory is requested at once: the parameters, this tile's record counts of
-    // all 29 channels (lane z holds cnt2[z][tile]; every warp the same copy) and the first channel's whole bin (its count
-    // is not known yet; 2 KB once per CTA)
+    // all 29 channels and the first two channels' whole bins (4 KB once per CTA)
     const size_t bin2_0 = ((size_t)(slot * S + sweep) * kZ) * kATTiles + tile;
-    uint32_t c_reg = 0;
-    if (lane < kZ) c_reg = __ldg(cnt2 + bin2_0 + (size_t)lane * kATTiles);
+    if (tid < kZ + 3) cN[tid] = tid < kZ ? __ldg(cnt2 + bin2_0 + (size_t)tid * kATTiles) : 0u;
     const uint2* binp = bins2 + bin2_0 * kATCap + tid;
-    cp_async_8(Rs + tid, binp);
+    cp_async_8(&Rs[0][tid], binp);                           // channels 0 and 1: whole bins, their counts are not known yet
     cp_async_commit();
-    binp += (size_t)kATTiles * kATCap;
+    cp_async_8(&Rs[1][tid], binp + (size_t)kATTiles * kATCap);
+    cp_async_commit();
+    binp += 2 * (size_t)kATTiles * kATCap;
     {
         const int* g = reinterpret_cast<const int*>(params + fsrc);
         int* s = reinterpret_cast<int*>(&P);
@@ -454,27 +462,31 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     if (SCL && tid < G.QH && T.yl[tid] - T.yf[tid] >= kATRows) __trap();
     const int FW = G.FW, FH = G.FH, fx0 = G.fx0, fy0 = G.fy0;
 
-    // records of channel z: one per thread, fetched one channel ahead straight into shared memory (cp.async: no
-    // registers held across the stages); each thread reads back only the slot it filled itself, so its own wait_group is
-    // all the ordering needed
-    auto load_records = [&](int z) -> uint32_t {
-        const uint32_t n = __shfl_sync(0xFFFFFFFFu, c_reg, z);
-        if ((uint32_t)tid < n && n <= (uint32_t)kATCap) cp_async_8(Rs + tid, binp);
-        cp_async_commit();
+    // records of channel z: one per thread, fetched TWO channels ahead straight into shared memory (cp.async: no registers
+    // held across the stages; one channel of lead does not cover the read latency under the kernel's own write stream);
+    // each thread reads back only the slots it filled itself, so its own wait_group is all the ordering needed
+    auto load_records = [&](int z) {
+        const uint32_t nz = cN[z];
+        if ((uint32_t)tid < nz && nz <= (uint32_t)kATCap) cp_async_8(&Rs[z & 1][tid], binp);
+        cp_async_commit();                                   // (an empty group keeps the wait_group arithmetic uniform)
         binp += (size_t)kATTiles * kATCap;
-        return n;
     };
-    uint32_t n = __shfl_sync(0xFFFFFFFFu, c_reg, 0);         // channel 0's records were requested at the top
     float* oplane = out + ((size_t)(fdst * S + sweep) * kZ) * kPlane + (size_t)oy0 * kW + ox0;
 
+#ifdef BEVGEN_AT_PROFILE
+    constexpr int PROF_TID = BEVGEN_AT_PROFILE;
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
 #pragma unroll 1
     for (int z = 0; z < kZ; ++z, oplane += kPlane) {
+        const uint32_t n = cN[z];
         const bool slow = n > (uint32_t)kATCap;              // uniform: over-full bin (dense scene)
         const uint32_t nw = slow ? 0u : n;
         // ---- A: records -> T0 (max) and the work list W --------------------------------------------------------------
-        cp_async_wait_all();
+        cp_async_wait_group<1>();                            // channel z has landed (z + 1 may still be in flight)
+        AT_TICK(0);
         if ((uint32_t)tid < nw) {
-            const uint2 rec = Rs[tid];
+            const uint2 rec = Rs[z & 1][tid];
             const int fx = (int)(rec.x & 1023u) - fx0, fy = (int)(rec.x >> 10) - fy0;       // inside the footprint by construction
             atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, rec.y);
             uint32_t w = at_pack_pos(fx, fy);
@@ -482,8 +494,11 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
             W[tid] = w;
         }
         if (slow && FW > 0) at_slow_fill(&SA, z, fx0, fy0, FW, FH, T0);
+        AT_TICK(1);
         __syncthreads();
-        if (z + 1 < kZ) n = load_records(z + 1);              // next channel's records: latency hidden behind B and C
+        AT_TICK(2);
+        load_records(z + 2);                                  // (Rs[z & 1] is free: every thread has read its slot)
+        AT_TICK(3);
         // ---- B: every non-zero source voxel -> the destination pixels it feeds -----------------------------------------
         if (ROT) {
             float* const D = SCL ? T1 : O;
@@ -522,7 +537,9 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
                 scl_row(G.dx0 + q - qy * G.DW, G.dy0 + qy, (int)(i - r * kATRows), G, T, T1, O, ox0, oy0, P.rects, nrect);
             }
         }
+        AT_TICK(4);
         __syncthreads();
+        AT_TICK(5);
         // ---- C: O -> HBM (each thread re-zeroes the float4s it has just read), clear the touched entries of T0 / T1 ------
         for (int i = tid; i < kATElems / 4; i += kATThreads) {
             const int r = i / (kATW / 4);
@@ -539,8 +556,13 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
             for (uint32_t i = tid; i < nw2; i += kATThreads) T1[W2[i]] = 0.f;
             if (tid == 0) nW2 = 0;                           // every thread took its copy (nw2) before the barrier above
         }
+        AT_TICK(6);
         __syncthreads();
+        AT_TICK(7);
     }
+#ifdef BEVGEN_AT_PROFILE
+    if (tid == PROF_TID) { for (int k = 0; k < 8; ++k) atomicAdd(&g_at_prof[k], (unsigned long long)prof[k]); atomicAdd(&g_at_prof[8], 1ull); }
+#endif
 }
 
 // Host: can k_tile_aug handle this frame's parameters?  Conservative real-valued bounds on the region sizes the kernel
