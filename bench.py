@@ -280,11 +280,17 @@ def run_ours(args) -> None:
 
     def run_e2e_pipelined(steps):
         h = pf.submit(batch)
-        for i in range(steps):
+        done = []                                   # completion events: the host stays at most 2 steps ahead of the GPU
+        for i in range(steps):                      # (bounded staging memory, as a training loop's own sync would impose)
+            if len(done) >= 2:
+                done.pop(0).synchronize()
             cur, h = h, (pf.submit(batch) if i + 1 < steps else None)
             ol, om = (out_l, out_m) if i % 2 == 0 else (out_l2, out_m2)
             r = pf.run(cur, aug, with_map=wl["map"], out_lidar=ol, out_map=om)
             probe_host.copy_(r["lidar_bev"][:, 14, 200, :], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            done.append(ev)
 
     def barrier():
         torch.cuda.synchronize()
