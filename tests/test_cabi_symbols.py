@@ -58,5 +58,23 @@ def test_argument_validation_without_a_gpu():
     # augmentation: in-place is refused
     assert L.bevgen_augment(one, one, 1, 3, one, one, null, 0, null) == INVALID
     assert L.bevgen_augment(one, C.c_void_p(32), 0, 3, one, one, null, 0, null) == INVALID
+    # generation fused with augmentation: host-side parameter screening, workspace sizing, argument checks
+    UNSUPPORTED = -3
+    from bevgen_b200 import augment as A
+    ok = A.pack_params([A.AugParams(angle_deg=15.0, scale=0.95), A.AugParams(angle_deg=-15.0, scale=1.05), A.AugParams(flip=True)])
+    bad = A.pack_params([A.AugParams(angle_deg=33.0)])
+    pk, pb = C.c_void_p(ok.ctypes.data), C.c_void_p(bad.ctypes.data)
+    assert L.bevgen_aug_fused_supported(pk, 3) == 1 and L.bevgen_aug_fused_supported(pb, 1) == 0
+    assert L.bevgen_aug_fused_supported(null, 1) == 0
+    base = L.bevgen_lidar_workspace_bytes(1000, 3, 10)
+    assert L.bevgen_lidar_aug_workspace_bytes(1000, 3, 10, 0) == base
+    assert L.bevgen_lidar_aug_workspace_bytes(1000, 3, 10, 2) >= base + 2 * 10 * 29 * 100 * 256 * 8     # per-tile record bins
+    assert L.bevgen_lidar_aug_workspace_bytes(1000, 3, 10, 4) == 0                                       # more than B frames
+    g = L.bevgen_lidar_bev_augmented
+    assert g(one, 0, one, one, 3, 10, 0, 0, one, null, one, one, 1 << 40, null) == INVALID               # no host copy of the params
+    assert g(null, 0, one, one, 3, 10, 5, 5, one, pk, one, one, 1 << 40, null) == INVALID                # points missing
+    assert g(C.c_void_p(8), 0, one, one, 3, 10, 0, 0, one, pk, one, one, 1 << 40, null) == INVALID       # float4 points must be 16-byte aligned
+    assert g(one, 0, one, one, 1, 10, 0, 0, one, pb, one, one, 1 << 40, null) == UNSUPPORTED             # refused, never approximated
+    assert g(one, 0, one, one, 3, 10, 0, 0, one, pk, one, one, 1024, null) == WORKSPACE
     for code in (INVALID, WORKSPACE, -3):
         assert L.bevgen_error_string(code).decode().startswith("bevgen:")

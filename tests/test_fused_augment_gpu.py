@@ -132,6 +132,17 @@ def test_grid_aligned_points_and_borders(bg, co):
         _check(bg, co, [f], [p], S=1)
 
 
+def test_frames_without_points_are_all_zero(bg):
+    """empty / missing sweeps (utils.py:75-76): every channel stays zero whatever the augmentation"""
+    import dataclasses
+    base = bg.synthetic.frame_c1(0, n=10)
+    empty = dataclasses.replace(base, points4=np.zeros((0, 4), np.float32), sweep_offsets=np.array([0, 0], np.int64))
+    batch, pts, off, tf = _pack(bg, [empty, empty], 2)
+    ps = [bg.AugParams(angle_deg=12.0, scale=0.97), bg.AugParams(scale=1.05, flip=True)]
+    got = bg.augment.lidar_bev_augmented(pts, off, tf, 2, 2, ps, max_sweep_points=batch.max_sweep_points)
+    assert got.shape == (2, 58, 400, 720) and not got.any().item()
+
+
 def test_unsupported_parameters_are_refused_not_approximated(bg):
     assert not bg.augment.fused_supported([bg.AugParams(angle_deg=40.0)])
     assert not bg.augment.fused_supported([bg.AugParams(scale=0.6)])

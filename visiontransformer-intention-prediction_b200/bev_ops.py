@@ -82,9 +82,9 @@ class _PinnedPool:
     buffer plus a host memcpy.  Instead the array returned IS a pinned buffer: the device->host copy runs at full PCIe rate
     straight into it, and the buffer goes back to the pool only when the array (and every view / ``torch.from_numpy`` alias
     of it) has been garbage-collected -- so no two live results ever share memory, which is all "fresh" means to a caller.
-    Small results (< 1 MiB) take the plain path."""
+    Small results (< 8 MiB, e.g. transform_points' output) take the plain path."""
 
-    MIN_BYTES = 1 << 20
+    MIN_BYTES = 8 << 20
     MAX_IDLE_BYTES = 8 << 30          # idle buffers kept for reuse; anything above is released to the OS
 
     def __init__(self) -> None:
