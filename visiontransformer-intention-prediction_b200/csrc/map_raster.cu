@@ -85,6 +85,61 @@ __device__ __forceinline__ short2 poly_vertex(const short2* L, int nl, const sho
     return p < nl ? L[p] : R[nr - 1 - (p - nl)];
 }
 
+// one interior row of fillPoly, the whole warp cooperating (any number of crossings); see fill_polygon
+__device__ void fill_row_cooperative(uint32_t* planes, uint32_t chmask, const short2* L, int nl, const short2* R, int nr,
+                                     int* xs, int* sorted, int lane, int y) {
+    const int n = nl + nr;
+    int k = 0;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        bool act = false;
+        int xc = 0;
+        if (e < n) {
+            const short2 p0 = poly_vertex(L, nl, R, nr, e == 0 ? n - 1 : e - 1), p1 = poly_vertex(L, nl, R, nr, e);
+            if (p0.y != p1.y) {
+                const short2 top = p0.y < p1.y ? p0 : p1, bot = p0.y < p1.y ? p1 : p0;
+                if (top.y <= y && y < bot.y) {
+                    const int dxfix = (((int)p1.x - (int)p0.x) * 65536) / ((int)p1.y - (int)p0.y);
+                    xc = (int)((long long)top.x * 65536 + (long long)(y - top.y) * dxfix);
+                    act = true;
+                }
+            }
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, act);
+        if (act) xs[k + __popc(m & ((1u << lane) - 1u))] = xc;
+        k += __popc(m);
+    }
+    __syncwarp();
+    if (k >= 2) {
+        // rank sort; ties broken by index -> a permutation
+        for (int i = lane; i < k; i += 32) {
+            const int xi = xs[i];
+            int r = 0;
+            for (int j = 0; j < k; ++j) { const int xj = xs[j]; r += (xj < xi) || (xj == xi && j < i); }
+            sorted[r] = xi;
+        }
+        __syncwarp();
+        for (int pidx = lane; 2 * pidx + 1 < k; pidx += 32) {
+            int xa = (sorted[2 * pidx] + 65535) >> 16, xb = sorted[2 * pidx + 1] >> 16;   // ceil left, floor right
+            if (xa < kW && xb >= 0) {
+                xa = max(xa, 0); xb = min(xb, kW - 1);
+                for (int w = xa >> 5; w <= (xb >> 5); ++w) {
+                    if (max(xa, w << 5) > min(xb, (w << 5) + 31)) continue;
+                    const int lo = max(xa, w << 5) & 31, hi = min(xb, (w << 5) + 31) & 31;
+                    const uint32_t bits = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+                    uint32_t cm = chmask;
+                    while (cm) {
+                        const int c = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        atomicOr(planes + c * kPlaneWords + y * kWordsPerRow + w, bits);
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // cv2.fillPoly of one contour: closed outline + even-odd scanline interior.
 __device__ void fill_polygon(uint32_t* planes, uint32_t chmask, const short2* L, int nl, const short2* R, int nr,
                              int* xs, int* sorted, int lane) {
@@ -102,58 +157,61 @@ __device__ void fill_polygon(uint32_t* planes, uint32_t chmask, const short2* L,
     // outline: edges v[e-1] -> v[e], closed
     for (int e = 0; e < n; ++e)
         draw_segment(planes, chmask, poly_vertex(L, nl, R, nr, e == 0 ? n - 1 : e - 1), poly_vertex(L, nl, R, nr, e), lane);
-    // interior: rows [ymin, ymax): an edge is active on [y_top, y_bottom)
-    for (int y = ymin; y < ymax; ++y) {
+    // interior: rows [ymin, ymax): an edge is active on [y_top, y_bottom).  One row per lane: every lane walks all edges
+    // (vertex reads are shared-memory broadcasts) and keeps its row's crossings sorted in registers; a chunk of 32 rows
+    // in which some row has more than kMaxCross crossings falls back to the warp-cooperative form below.
+    constexpr int kMaxCross = 8;
+    for (int y0 = ymin; y0 < ymax; y0 += 32) {
+        const int y = y0 + lane;
+        const bool row_on = y < ymax;
+        int xr[kMaxCross];
+#pragma unroll
+        for (int j = 0; j < kMaxCross; ++j) xr[j] = 0x7FFFFFFF;
         int k = 0;
-        for (int e0 = 0; e0 < n; e0 += 32) {
-            const int e = e0 + lane;
-            bool act = false;
-            int xc = 0;
-            if (e < n) {
-                const short2 p0 = poly_vertex(L, nl, R, nr, e == 0 ? n - 1 : e - 1), p1 = poly_vertex(L, nl, R, nr, e);
-                if (p0.y != p1.y) {
-                    const short2 top = p0.y < p1.y ? p0 : p1, bot = p0.y < p1.y ? p1 : p0;
-                    if (top.y <= y && y < bot.y) {
-                        // dx = trunc(((x1 - x0) << 16) / (y1 - y0)) with (P0,P1) in contour order (C division)
-                        const int dxfix = (((int)p1.x - (int)p0.x) * 65536) / ((int)p1.y - (int)p0.y);
-                        xc = (int)((long long)top.x * 65536 + (long long)(y - top.y) * dxfix);
-                        act = true;
+        short2 p0 = poly_vertex(L, nl, R, nr, n - 1);
+        for (int e = 0; e < n; ++e) {
+            const short2 p1 = poly_vertex(L, nl, R, nr, e);
+            if (p0.y != p1.y) {                                               // uniform
+                const short2 top = p0.y < p1.y ? p0 : p1, bot = p0.y < p1.y ? p1 : p0;
+                if (row_on && top.y <= y && y < bot.y) {
+                    // dx = trunc(((x1 - x0) << 16) / (y1 - y0)) with (P0,P1) in contour order (C division)
+                    const int dxfix = (((int)p1.x - (int)p0.x) * 65536) / ((int)p1.y - (int)p0.y);
+                    int v = (int)((long long)top.x * 65536 + (long long)(y - top.y) * dxfix);
+                    ++k;
+                    // insert into the sorted register array (unrolled; a value pushed past the end is dropped, k remembers it)
+#pragma unroll
+                    for (int j = 0; j < kMaxCross; ++j) {
+                        const int lo = min(xr[j], v);
+                        v = max(xr[j], v);
+                        xr[j] = lo;
                     }
                 }
             }
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, act);
-            if (act) xs[k + __popc(m & ((1u << lane) - 1u))] = xc;
-            k += __popc(m);
+            p0 = p1;
         }
-        __syncwarp();
-        if (k >= 2) {
-            // rank sort (k is tiny: 2-4 for lane polygons); ties broken by index -> a permutation
-            for (int i = lane; i < k; i += 32) {
-                const int xi = xs[i];
-                int r = 0;
-                for (int j = 0; j < k; ++j) { const int xj = xs[j]; r += (xj < xi) || (xj == xi && j < i); }
-                sorted[r] = xi;
-            }
-            __syncwarp();
-            for (int pidx = lane; 2 * pidx + 1 < k; pidx += 32) {
-                int xa = (sorted[2 * pidx] + 65535) >> 16, xb = sorted[2 * pidx + 1] >> 16;   // ceil left, floor right
-                if (xa < kW && xb >= 0) {
-                    xa = max(xa, 0); xb = min(xb, kW - 1);
-                    for (int w = xa >> 5; w <= (xb >> 5); ++w) {
-                        const int lo = max(xa, w << 5) & 31, hi = min(xb, (w << 5) + 31) & 31;
-                        if (max(xa, w << 5) > min(xb, (w << 5) + 31)) continue;
-                        const uint32_t bits = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
-                        uint32_t cm = chmask;
-                        while (cm) {
-                            const int c = __ffs(cm) - 1;
-                            cm &= cm - 1;
-                            atomicOr(planes + c * kPlaneWords + y * kWordsPerRow + w, bits);
-                        }
+        if (__any_sync(0xFFFFFFFFu, k > kMaxCross)) {
+            for (int yy = y0; yy < min(y0 + 32, ymax); ++yy) fill_row_cooperative(planes, chmask, L, nl, R, nr, xs, sorted, lane, yy);
+            continue;
+        }
+#pragma unroll
+        for (int pidx = 0; pidx < kMaxCross / 2; ++pidx) {
+            if (2 * pidx + 1 >= k) break;
+            int xa = (xr[2 * pidx] + 65535) >> 16, xb = xr[2 * pidx + 1] >> 16;   // ceil left, floor right
+            if (xa < kW && xb >= 0) {
+                xa = max(xa, 0); xb = min(xb, kW - 1);
+                for (int w = xa >> 5; w <= (xb >> 5); ++w) {
+                    if (max(xa, w << 5) > min(xb, (w << 5) + 31)) continue;
+                    const int lo = max(xa, w << 5) & 31, hi = min(xb, (w << 5) + 31) & 31;
+                    const uint32_t bits = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+                    uint32_t cm = chmask;
+                    while (cm) {
+                        const int c = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        atomicOr(planes + c * kPlaneWords + y * kWordsPerRow + w, bits);
                     }
                 }
             }
         }
-        __syncwarp();
     }
 }
 
@@ -200,32 +258,49 @@ __global__ void __launch_bounds__(kDrawThreads) k_map_draw(MapIn in, uint32_t* _
 }
 
 // bit planes -> float32, 4 pixels per thread (one float4 store); flip + dropout fused
-__global__ void __launch_bounds__(256) k_map_expand(const uint32_t* __restrict__ bitplanes, float* __restrict__ out,
+// One short-lived 128-thread CTA per (frame, channel, band of 10 rows) = 28 800 contiguous output bytes: the band's 240
+// bit-plane words -> a float32 tile in shared memory -> ONE TMA bulk store (the shape that reaches 7.5 TB/s for the
+// LiDAR tiles, lidar.cu); flip (utils.py:399-400) and dropout rectangles (utils.py:496-497) fused.
+constexpr int kExpRows = 10;
+constexpr int kExpBytes = kExpRows * kW * 4;            // 28 800
+constexpr int kExpBands = kH / kExpRows;                // 40
+__global__ void __launch_bounds__(128) k_map_expand(const uint32_t* __restrict__ bitplanes, float* __restrict__ out,
                                                     const uint8_t* __restrict__ flip, const int32_t* __restrict__ rects,
-                                                    const int32_t* __restrict__ nrects, long long total4) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= total4) return;
-    constexpr int kRow4 = kW / 4;                       // 180 float4 per row
-    const int x4 = (int)(i % kRow4);
-    const long long r = i / kRow4;                      // (b*9 + c)*400 + y
-    const int y = (int)(r % kH);
-    const long long bc = r / kH;
-    const int b = (int)(bc / kMapC);
+                                                    const int32_t* __restrict__ nrects) {
+    extern __shared__ __align__(128) unsigned char mtile[];
+    __shared__ uint32_t words[kExpRows * kWordsPerRow];
+    __shared__ int sRect[kMaxRects * 4];
+    const int tid = threadIdx.x;
+    const unsigned t = blockIdx.x;                      // (b*9 + c)*40 + band
+    const unsigned bc = t / kExpBands, band = t - bc * kExpBands, b = bc / kMapC;
+    const int y0 = (int)band * kExpRows;
+    const uint32_t* src = bitplanes + (size_t)bc * kPlaneWords + y0 * kWordsPerRow;
+    for (int i = tid; i < kExpRows * kWordsPerRow; i += 128) words[i] = __ldg(src + i);
     const bool fl = flip ? (flip[b] != 0) : false;
     int nr = nrects ? nrects[b] : 0;
     nr = nr > kMaxRects ? kMaxRects : nr;
-    const int* rc = rects ? rects + (size_t)b * kMaxRects * 4 : nullptr;
-    const uint32_t* row = bitplanes + (size_t)bc * kPlaneWords + y * kWordsPerRow;
-    float v[4];
+    if (tid < 4 * nr) sRect[tid] = rects[(size_t)b * kMaxRects * 4 + tid];
+    __syncthreads();
+    constexpr int kRow4 = kW / 4;                       // 180 float4 per row
+    for (int i = tid; i < kExpRows * kRow4; i += 128) {
+        const int yl = i / kRow4, x4 = i - yl * kRow4;
+        float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int x = 4 * x4 + j;
-        const int sx = fl ? kW - 1 - x : x;             // utils.py:399-400
-        bool on = (row[sx >> 5] >> (sx & 31)) & 1u;
-        if (on && nr && in_rects(rc, nr, y, x)) on = false;    // utils.py:496-497
-        v[j] = on ? 1.0f : 0.0f;
+        for (int j = 0; j < 4; ++j) {
+            const int x = 4 * x4 + j;
+            const int sx = fl ? kW - 1 - x : x;         // utils.py:399-400
+            bool on = (words[yl * kWordsPerRow + (sx >> 5)] >> (sx & 31)) & 1u;
+            if (on && nr && in_rects(sRect, nr, y0 + yl, x)) on = false;    // utils.py:496-497
+            v[j] = on ? 1.0f : 0.0f;
+        }
+        reinterpret_cast<float4*>(mtile)[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
-    reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid != 0) return;
+    bulk_store_s2g(reinterpret_cast<unsigned char*>(out) + (size_t)t * kExpBytes, mtile, kExpBytes);
+    bulk_commit();
+    bulk_wait_read<0>();
 }
 
 struct Mat3 { double m[9]; };
@@ -273,9 +348,9 @@ extern "C" int bevgen_map_raster(const double* verts, const int32_t* pl_off, con
         const dim3 grid((max_prims + kDrawWarps - 1) / kDrawWarps, B);
         BEVGEN_LAUNCH("k_map_draw", st, k_map_draw<<<grid, kDrawThreads, smem, st>>>(in, planes, maxv));
     }
-    const long long total4 = (long long)B * kMapC * kH * (kW / 4);
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;      // TMA bulk stores need 16 B alignment
     BEVGEN_LAUNCH("k_map_expand", st,
-                  k_map_expand<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(planes, out, flip, drop_rects, drop_counts, total4));
+                  k_map_expand<<<(unsigned)(B * kMapC * kExpBands), 128, kExpBytes, st>>>(planes, out, flip, drop_rects, drop_counts));
     return 0;
 }
 

@@ -98,7 +98,7 @@ class BevGenerator:
     """Owns the device-side state (map table, workspaces) and turns FrameBatches into model inputs."""
 
     def __init__(self, map_table: Optional[map_ops.MapTable] = None, algo: int = bev_ops.ALGO_TILED,
-                 device: Optional[torch.device] = None, fused_augment: bool = True) -> None:
+                 device: Optional[torch.device] = None, fused_augment: bool = True, map_stream_priority: int = 0) -> None:
         self.device = device or bev_ops._require_cuda()
         self.map_table = map_table
         self.algo = algo
@@ -108,7 +108,8 @@ class BevGenerator:
         self._scratch = {}
         # the map rasterizer is independent of the LiDAR kernels and far from saturating the GPU (one warp per lane
         # segment): it runs on a side stream and is joined before the tensors are handed out
-        self._map_stream = torch.cuda.Stream(device=self.device)
+        # (measured on config 3: default priority 16 700 frames/s; a high-priority map stream delays the binning pass: 16 440)
+        self._map_stream = torch.cuda.Stream(device=self.device, priority=map_stream_priority)
 
     def _buf(self, key, shape) -> torch.Tensor:
         t = self._scratch.get(key)
