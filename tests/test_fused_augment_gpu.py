@@ -163,3 +163,28 @@ def test_generator_routes_through_fused_kernel_and_matches_dense_route(bg):
     b = bg.BevGenerator(table, fused_augment=False).generate(batch, aug)
     assert torch.equal(a["lidar_bev"], b["lidar_bev"])
     assert torch.equal(a["map_bev"], b["map_bev"])
+
+
+def test_every_parameter_set_the_host_accepts_runs_and_matches_the_dense_route(bg):
+    """the host screening (bevgen_aug_fused_supported) is conservative: whatever it lets through must fit the kernel's
+    shared-memory tiles (the kernel traps otherwise) and give the dense route's bits -- swept past the reference's ranges"""
+    f = bg.synthetic.frame_c2(3, n=20_000, S=1)
+    fb = bg.FrameBatch.pack([f], 1)
+    dev = torch.device("cuda")
+    pts, off, tf = fb.points4.to(dev), fb.sweep_offsets.to(dev), fb.rel_tf.to(dev)
+    plain = bg.lidar_bev_from_sweeps(pts, off, tf, 1, 1, max_sweep_points=fb.max_sweep_points)
+    accepted = refused = 0
+    for angle in (None, 15.2, -15.6, 16.0, -16.4, 17.0, 19.0, -25.0):
+        for scale in (None, 0.90, 0.93, 0.94, 0.949, 1.051, 1.06, 1.08, 1.15):
+            if angle is None and scale is None:
+                continue
+            p = bg.AugParams(angle_deg=angle, scale=scale, flip=(accepted % 2 == 0))
+            if not bg.augment.fused_supported([p]):
+                refused += 1
+                continue
+            accepted += 1
+            got = bg.augment.lidar_bev_augmented(pts, off, tf, 1, 1, [p], max_sweep_points=fb.max_sweep_points)
+            want = bg.augment_grid(plain, [p])
+            assert torch.equal(got, want), (angle, scale)
+    torch.cuda.synchronize()
+    assert accepted >= 8 and refused >= 8, (accepted, refused)
