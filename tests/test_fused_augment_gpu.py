@@ -188,3 +188,22 @@ def test_every_parameter_set_the_host_accepts_runs_and_matches_the_dense_route(b
             assert torch.equal(got, want), (angle, scale)
     torch.cuda.synchronize()
     assert accepted >= 8 and refused >= 8, (accepted, refused)
+
+
+def test_repeated_runs_are_bit_identical_at_full_size(bg):
+    """functional race check (compute-sanitizer is not available on the pool): 25 back-to-back runs of the fused path on
+    BASELINE-size frames, sparse and clustered, must give one and the same grid -- a missing barrier or a racy shared-memory
+    clear shows up as a run-to-run difference"""
+    frames = [bg.synthetic.frame_c2(200), bg.synthetic.frame_c4(200), bg.synthetic.frame_c2(201), bg.synthetic.frame_c2(202)]
+    aug = [bg.AugParams(angle_deg=14.0, flip=True), bg.AugParams(angle_deg=-7.0, scale=1.03),
+           bg.AugParams(scale=0.955, rects=[(100, 100, 50, 50)]), bg.AugParams(angle_deg=3.0, scale=0.99)]
+    fb = bg.FrameBatch.pack(frames, 10)
+    dev = torch.device("cuda")
+    pts, off, tf = fb.points4.to(dev), fb.sweep_offsets.to(dev), fb.rel_tf.to(dev)
+    first = bg.augment.lidar_bev_augmented(pts, off, tf, 4, 10, aug, max_sweep_points=fb.max_sweep_points).clone()
+    out = torch.empty_like(first)
+    for _ in range(25):
+        bg.augment.lidar_bev_augmented(pts, off, tf, 4, 10, aug, max_sweep_points=fb.max_sweep_points, out=out)
+        assert torch.equal(out, first)
+    dense = bg.augment_grid(bg.lidar_bev_from_sweeps(pts, off, tf, 4, 10, max_sweep_points=fb.max_sweep_points), aug)
+    assert torch.equal(first, dense)
