@@ -58,3 +58,25 @@ def test_augment_bev_golden(bg):
         assert np.array_equal(mo, dense(z, f"s{sd}_map")), int(sd)
         assert np.array_equal(g2["boxes_xywha"].numpy(), z[f"s{sd}_boxes"]), int(sd)
         assert np.array_equal(g2["intentions"].numpy(), z[f"s{sd}_intents"]), int(sd)
+
+
+def test_fused_generation_plus_augmentation_golden(bg):
+    """bevgen_lidar_bev_augmented (augmented grid built straight from the point records) reproduces the reference's own
+    outputs for transform_points -> create_intentnet_lidar_bev -> seeded augment_bev (tests/golden/fused_chain.npz)"""
+    z = load("fused_chain.npz")
+    S = int(z["rel_tf"].shape[0])
+    dev = torch.device("cuda")
+    seeds = [int(s) for s in z["seeds"]]
+    params = []
+    for sd in seeds:
+        random.seed(sd)
+        params.append(bg.draw_aug_params(random))
+    B = len(seeds)
+    pts = torch.from_numpy(np.tile(z["points4"], (B, 1))).to(dev)
+    n = z["points4"].shape[0]
+    off = np.concatenate([[0], np.concatenate([b * n + z["sweep_offsets"][1:] for b in range(B)])]).astype(np.int32)
+    tf = torch.from_numpy(np.tile(z["rel_tf"].reshape(S, 16), (B, 1))).to(dev)
+    mx = int(np.diff(z["sweep_offsets"]).max())
+    got = bg.augment.lidar_bev_augmented(pts, torch.from_numpy(off).to(dev), tf, B, S, params, max_sweep_points=mx).cpu().numpy()
+    for b, sd in enumerate(seeds):
+        assert np.array_equal(got[b], dense(z, f"s{sd}")), (sd, params[b])
