@@ -91,7 +91,8 @@ int bevgen_transform_points_f64(const double *pts, int64_t n, int64_t stride, co
  * max_sweep_points: max over sweeps of the row count (host knows it; sizes the grid).
  * algo: BEVGEN_ALGO_TILED          one binning pass into per-tile record bins; per 28.8 KB tile one CTA builds the tile
  *                                  in shared memory (warp-aggregated atomicMax) and writes it with ONE TMA bulk store
- *       BEVGEN_ALGO_ATOMIC         TMA zero-fill kernel + global RED.MAX scatter kernel              [fastest, default]
+ *                                  [default of the Python layer; fastest except on dense / skewed scenes]
+ *       BEVGEN_ALGO_ATOMIC         TMA zero-fill kernel + global RED.MAX scatter kernel
  *       BEVGEN_ALGO_MEMSET_ATOMIC  cudaMemsetAsync + the same scatter kernel (library fill; comparison point)
  *       All produce identical bits; a workspace is needed for TILED only.
  * ------------------------------------------------------------------------------------- */

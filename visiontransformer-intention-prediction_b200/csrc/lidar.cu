@@ -4,15 +4,18 @@
 //   transform_points            reference utils.py:27-33   (per sweep, dataset.py:339-340)
 //   create_intentnet_lidar_bev  reference utils.py:62-106
 //
-// Two algorithms, identical bits (DESIGN.md section 3.1 has the measurements and the variants that were tried
-// and removed):
-//   ATOMIC (default)  k_zero_fill_tma   one short-lived CTA per 28.8 KB chunk: TMA bulk store of a zero tile
-//                     k_scatter_atomic  one thread per point: FP64 pose FMA chain, exact binning, RED.MAX into the grid
-//   TILED             k_bin_fixed       one pass: points -> fixed-capacity per-tile record bins (+ overflow list)
+// Three selectable algorithms, identical bits (DESIGN.md section 3.1 has the measurements and the variants that were
+// tried and removed):
+//   TILED (default)   k_bin_fixed       one pass: points -> fixed-capacity per-tile record bins (+ per-sweep overflow lists)
 //                     k_tile_store      one short-lived CTA per 28.8 KB tile: shared-memory tile, warp-aggregated
 //                                       (__match_any_sync) atomicMax, ONE TMA bulk store -- each output byte written once
 //                     k_overflow_red    overflow records as global RED.MAX
+//   ATOMIC            k_zero_fill_tma   one short-lived CTA per 28.8 KB chunk: TMA bulk store of a zero tile
+//                     k_scatter_atomic  one thread per point: FP64 pose FMA chain, exact binning, RED.MAX into the grid
+//                                       (faster on dense / skewed scenes, where the tile bins overflow)
 //   MEMSET_ATOMIC     cudaMemsetAsync + k_scatter_atomic (library fill; kept only as a comparison point)
+// and, on top of the tiled path's record bins, generation FUSED with the resampling augmentations (lidar_aug_tile.cuh:
+// k_rebin_aug + k_tile_aug), entry point bevgen_lidar_bev_augmented.
 #include "aug_geom.cuh"
 
 #include <cuda_fp16.h>
