@@ -89,7 +89,6 @@ struct AugTileTables {
 struct RotFwd { float f00, f01, f02, f10, f11, f12, hx, hy; };
 struct SclFwd { float sfx, sfy, offx, offy; };
 constexpr int kATCand = 9;                                   // rotation candidates per source voxel (3 x 3; kernel traps unless hx, hy < 1.5)
-constexpr int kATRows = 3;                                   // resize: output rows per source pixel (<= 3 for scale factors < 1.45)
 constexpr int kATOrgBias = 64;
 
 __device__ __forceinline__ RotFwd make_rot_fwd(const double* __restrict__ M) {
@@ -295,12 +294,38 @@ __device__ __forceinline__ void rot_candidate(uint32_t w_, int c, const AugTileG
     // every writer of a pixel writes the same value; the one that finds it still zero lists it (a pixel whose value
     // is zero needs no further work: it equals an untouched one)
     const uint32_t old = atomicExch(reinterpret_cast<uint32_t*>(D) + di, __float_as_uint(val));
-    if (old == 0u && __float_as_uint(val) != 0u) W2[atomicAdd(nW2, 1u)] = (uint16_t)di;
+    if (old == 0u && __float_as_uint(val) != 0u) W2[atomicAdd(nW2, 1u)] = (uint16_t)((ly << 7) | lx);   // (DW <= 80, DH <= 48)
 }
 
-// Source pixel (u, v) of the resize (coordinates of the image being resized), r-th of the output rows it feeds: evaluate
-// every output pixel of that row whose 2 x 2 taps include it (exactly the columns [xf, xl] of the inverse tap table).
-// src = tile holding the region [qx0, qx0+QW) x [qy0, qy0+QH), row stride QW.
+// Source pixel (u, v) of the resize (coordinates of the image being resized), work item q (0..3) of it: the output pixels
+// whose 2 x 2 taps include the pixel are exactly the rows [yf, yl] x columns [xf, xl] of the inverse tap tables -- 2 x 2 of
+// them as a rule, so item q = (row yf + (q >> 1), column xf + (q & 1)) evaluates ONE output pixel; the items with a set bit
+// also take the rare third row / column.  src = tile holding the region [qx0, qx0+QW) x [qy0, qy0+QH), row stride QW.
+constexpr int kATQuad = 4;
+__device__ __forceinline__ void scl_quad(int u, int v, int q, const AugTileGeo& G, const AugTileTables& T,
+                                         const float* __restrict__ src, float* __restrict__ O, int ox0, int oy0,
+                                         const int* rects, int nrect) {
+    const int ry = q >> 1, rx = q & 1;
+    const int yl = T.yl[v - G.qy0], xl = T.xl[u - G.qx0];
+    const int ly0 = T.yf[v - G.qy0] + ry, lx0 = T.xf[u - G.qx0] + rx;
+    const int ly1 = ry ? yl : min(ly0, yl), lx1 = rx ? xl : min(lx0, xl);
+    for (int ly = ly0; ly <= ly1; ++ly) {
+        const int b0 = T.s0y[ly], b1 = T.s1y[ly];
+        const float wy0 = T.wy0[ly], wy1 = T.wy1[ly];
+        const float* r0 = src + (b0 - G.qy0) * G.QW - G.qx0;
+        const float* r1 = src + (b1 - G.qy0) * G.QW - G.qx0;
+        for (int lx = lx0; lx <= lx1; ++lx) {
+            if (nrect && in_rects(rects, nrect, oy0 + ly, ox0 + lx)) continue;                  // utils.py:496
+            const int a0 = T.s0x[lx], a1 = T.s1x[lx];
+            O[ly * kATW + lx] = resize_sum(r0[a0], r0[a1], r1[a0], r1[a1], T.wx0[lx], T.wx1[lx], wy0, wy1);
+        }
+    }
+}
+
+// The same by rows: r-th (0..2) of the output rows source pixel (u, v) feeds, all its columns.  Measured per class on B200:
+// scale-only frames are faster with 3 row items per record (73 vs 77 us per frame), rotate + scale frames with 4 quad
+// items per listed T1 pixel (159 vs 176 us).
+constexpr int kATRows = 3;
 __device__ __forceinline__ void scl_row(int u, int v, int r, const AugTileGeo& G, const AugTileTables& T,
                                         const float* __restrict__ src, float* __restrict__ O, int ox0, int oy0,
                                         const int* rects, int nrect) {
@@ -458,8 +483,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     }
     for (int i = tid; i < (kATElems + Cfg::kT0 + Cfg::kT1) / 4; i += kATThreads) reinterpret_cast<float4*>(at_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    if (SCL && tid < G.QW && T.xl[tid] - T.xf[tid] >= 8) __trap();           // (never for scale factors anywhere near 1)
-    if (SCL && tid < G.QH && T.yl[tid] - T.yf[tid] >= kATRows) __trap();
+    if (SCL && !ROT && tid < G.QH && T.yl[tid] - T.yf[tid] >= kATRows) __trap();   // (scale factors >= 1.45; the host refuses them)
     const int FW = G.FW, FH = G.FH, fx0 = G.fx0, fy0 = G.fy0;
 
     // records of channel z: one per thread, fetched TWO channels ahead straight into shared memory (cp.async: no registers
@@ -500,7 +524,13 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         load_records(z + 2);                                  // (Rs[z & 1] is free: every thread has read its slot)
         AT_TICK(3);
         // ---- B: every non-zero source voxel -> the destination pixels it feeds -----------------------------------------
-        if (ROT) {
+#ifdef BEVGEN_AT_SKIP_B
+        constexpr bool kDoB = false;                          // timing experiment only: leaves the output wrong
+#else
+        constexpr bool kDoB = true;
+#endif
+        if (!kDoB) {
+        } else if (ROT) {
             float* const D = SCL ? T1 : O;
             if (!slow) {
                 for (uint32_t i = tid; i < nw * kATCand; i += kATThreads) {
@@ -531,10 +561,9 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         if (ROT && SCL) {
             __syncthreads();
             nw2 = nW2;                                        // T1's non-zero pixels, each listed once
-            for (uint32_t i = tid; i < nw2 * kATRows; i += kATThreads) {
-                const uint32_t r = i / kATRows;
-                const int q = W2[r], qy = q / G.DW;
-                scl_row(G.dx0 + q - qy * G.DW, G.dy0 + qy, (int)(i - r * kATRows), G, T, T1, O, ox0, oy0, P.rects, nrect);
+            for (uint32_t i = tid; i < nw2 * kATQuad; i += kATThreads) {
+                const int w = W2[i / kATQuad];
+                scl_quad(G.dx0 + (w & 127), G.dy0 + (w >> 7), (int)(i % kATQuad), G, T, T1, O, ox0, oy0, P.rects, nrect);
             }
         }
         AT_TICK(4);
@@ -553,7 +582,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
             for (int i = tid; i < Cfg::kT0 / 4; i += kATThreads) reinterpret_cast<float4*>(T0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (ROT && SCL) {
-            for (uint32_t i = tid; i < nw2; i += kATThreads) T1[W2[i]] = 0.f;
+            for (uint32_t i = tid; i < nw2; i += kATThreads) { const int w = W2[i]; T1[(w >> 7) * G.DW + (w & 127)] = 0.f; }
             if (tid == 0) nW2 = 0;                           // every thread took its copy (nw2) before the barrier above
         }
         AT_TICK(6);
