@@ -153,16 +153,33 @@ __device__ __forceinline__ AugTileGeo aug_tile_geo(const bevgen_aug_params& P, i
     return G;
 }
 
+// A work-list entry packs the voxel's footprint position (7 + 7 bits: the footprint is at most 127 x 127, checked) and,
+// for the rotation, the origin of its candidate window relative to the destination region (8 + 8 bits, biased).  The
+// re-binning kernel writes the entry into the per-tile record, so the tile kernel only unpacks it.
+__device__ __forceinline__ uint32_t at_pack_pos(int fx, int fy) { return ((uint32_t)fy << 7) | (uint32_t)fx; }
+__device__ __forceinline__ int at_pos_x(uint32_t w) { return (int)(w & 127u); }
+__device__ __forceinline__ int at_pos_y(uint32_t w) { return (int)((w >> 7) & 127u); }
+__device__ __forceinline__ uint32_t rot_window_origin_at(float cx, float cy, const RotFwd& F, int dx0, int dy0) {
+    const int xr = min(max((int)ceilf(cx - F.hx) - dx0 + kATOrgBias, 0), 255);   // clamped windows lie outside the region
+    const int yr = min(max((int)ceilf(cy - F.hy) - dy0 + kATOrgBias, 0), 255);
+    return ((uint32_t)yr << 22) | ((uint32_t)xr << 14);
+}
+__device__ __forceinline__ uint32_t rot_window_origin(int u, int v, const RotFwd& F, const AugTileGeo& G) {
+    const float cx = fmaf(F.f00, (float)u, fmaf(F.f01, (float)v, F.f02)), cy = fmaf(F.f10, (float)u, fmaf(F.f11, (float)v, F.f12));
+    return rot_window_origin_at(cx, cy, F, G.dx0, G.dy0);
+}
+
 // ---- re-binning: row-band bins -> per-(channel, output tile) bins ---------------------------------------------------
-// grid (29 channels, S sweeps, frames of the class); record = (u | v << 10, intensity bits), source pixel (u, v)
+// grid (29 channels, S sweeps, frames of the class); record = (work-list entry of the source pixel for that tile, intensity bits)
 template <bool ROT, bool SCL>
-__global__ void __launch_bounds__(kRebinThreads) k_rebin_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
+__global__ void __launch_bounds__(kRebinThreads, 4) k_rebin_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
                                                           const uint32_t* __restrict__ ovf_cnt, const OvfRec* __restrict__ ovf,
                                                           const int32_t* __restrict__ sweep_off,
                                                           uint32_t* __restrict__ cnt2, uint2* __restrict__ bins2,
                                                           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S) {
     __shared__ bevgen_aug_params P;
     __shared__ int4 box[kATTiles];                           // footprint of each output tile: x0, y0, x1, y1 (inclusive)
+    __shared__ short2 dorg[kATTiles];                        // origin of its rotation destination region
     __shared__ uint32_t hist[kATTiles];
     __shared__ int s_over;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -178,6 +195,7 @@ __global__ void __launch_bounds__(kRebinThreads) k_rebin_aug(const uint32_t* __r
     for (int t = tid; t < kATTiles; t += kRebinThreads) {
         const AugTileGeo G = aug_tile_geo<ROT, SCL>(P, (t % kATBX) * kATW, (t / kATBX) * kATH);
         box[t] = make_int4(G.fx0, G.fy0, G.fx0 + G.FW - 1, G.fy0 + G.FH - 1);
+        dorg[t] = make_short2((short)G.dx0, (short)G.dy0);
         hist[t] = 0;
     }
     constexpr int kCandY = (36 + kATH - 1) / kATH;           // 1 tile row either side at 40-row tiles, 2 at 20-row tiles
@@ -210,10 +228,10 @@ __global__ void __launch_bounds__(kRebinThreads) k_rebin_aug(const uint32_t* __r
         // bounding box reaches < 36 rows / columns beyond the tile's own image, host-checked) are the candidates
         float px = (float)u, py = (float)v;
         if (ROT) { const float qx = fmaf(RF.f00, px, fmaf(RF.f01, py, RF.f02)); py = fmaf(RF.f10, px, fmaf(RF.f11, py, RF.f12)); px = qx; }
+        const float rcx = px, rcy = py;                      // centre of the rotation's candidate window (rot_window_origin)
         if (SCL) { px = (px + 0.5f) * SF.sfx - 0.5f + SF.offx; py = (py + 0.5f) * SF.sfy - 0.5f + SF.offy; }
         const int tx = min(max((int)floorf(px * (1.0f / kATW)), 0), kATBX - 1);
         const int ty = min(max((int)floorf(py * (1.0f / kATH)), 0), kATBY - 1);
-        const uint2 o = make_uint2((uint32_t)u | ((uint32_t)v << 10), rec.y);
 #pragma unroll
         for (int dy = -kCandY; dy <= kCandY; ++dy)
 #pragma unroll
@@ -224,7 +242,11 @@ __global__ void __launch_bounds__(kRebinThreads) k_rebin_aug(const uint32_t* __r
                 const int4 b = box[t];
                 if (u < b.x || u > b.z || v < b.y || v > b.w) continue;
                 const uint32_t s = atomicAdd(&hist[t], 1u);
-                if (s < (uint32_t)kATCap) out_base[(size_t)t * kATCap + s] = o;
+                if (s < (uint32_t)kATCap) {
+                    uint32_t w = at_pack_pos(u - b.x, v - b.y);
+                    if (ROT) w |= rot_window_origin_at(rcx, rcy, RF, dorg[t].x, dorg[t].y);
+                    out_base[(size_t)t * kATCap + s] = make_uint2(w, rec.y);
+                }
             }
     };
 #pragma unroll
@@ -250,18 +272,6 @@ __global__ void __launch_bounds__(kRebinThreads) k_rebin_aug(const uint32_t* __r
     // a count above kATCap sends that (channel, tile) down the tile kernel's slow path
     for (int t = tid; t < kATTiles; t += kRebinThreads)
         cnt2[((size_t)(slot * S + sweep) * kZ + zb) * kATTiles + t] = hist[t];
-}
-
-// A work-list entry packs the voxel's footprint position (7 + 7 bits: the footprint is at most 127 x 127, checked) and,
-// for the rotation, the origin of its candidate window relative to the destination region (8 + 8 bits, biased).
-__device__ __forceinline__ uint32_t at_pack_pos(int fx, int fy) { return ((uint32_t)fy << 7) | (uint32_t)fx; }
-__device__ __forceinline__ int at_pos_x(uint32_t w) { return (int)(w & 127u); }
-__device__ __forceinline__ int at_pos_y(uint32_t w) { return (int)((w >> 7) & 127u); }
-__device__ __forceinline__ uint32_t rot_window_origin(int u, int v, const RotFwd& F, const AugTileGeo& G) {
-    const float cx = fmaf(F.f00, (float)u, fmaf(F.f01, (float)v, F.f02)), cy = fmaf(F.f10, (float)u, fmaf(F.f11, (float)v, F.f12));
-    const int xr = min(max((int)ceilf(cx - F.hx) - G.dx0 + kATOrgBias, 0), 255);   // clamped windows lie outside the region
-    const int yr = min(max((int)ceilf(cy - F.hy) - G.dy0 + kATOrgBias, 0), 255);
-    return ((uint32_t)yr << 22) | ((uint32_t)xr << 14);
 }
 
 // Candidate c (0..8) of the source voxel of work-list entry w (position + window origin): if that
@@ -510,12 +520,9 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         cp_async_wait_group<1>();                            // channel z has landed (z + 1 may still be in flight)
         AT_TICK(0);
         if ((uint32_t)tid < nw) {
-            const uint2 rec = Rs[z & 1][tid];
-            const int fx = (int)(rec.x & 1023u) - fx0, fy = (int)(rec.x >> 10) - fy0;       // inside the footprint by construction
-            atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, rec.y);
-            uint32_t w = at_pack_pos(fx, fy);
-            if (ROT) w |= rot_window_origin(fx0 + fx, fy0 + fy, RF, G);
-            W[tid] = w;
+            const uint2 rec = Rs[z & 1][tid];                // (work-list entry, intensity bits), inside the footprint by construction
+            atomicMax(reinterpret_cast<uint32_t*>(T0) + at_pos_y(rec.x) * FW + at_pos_x(rec.x), rec.y);
+            W[tid] = rec.x;
         }
         if (slow && FW > 0) at_slow_fill(&SA, z, fx0, fy0, FW, FH, T0);
         AT_TICK(1);
