@@ -190,6 +190,16 @@ int bevgen_lidar_bev_augmented(const void *pts, int pts_f16, const int32_t *swee
                                const bevgen_aug_params *params, const bevgen_aug_params *params_host,
                                float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
 
+/* rasterize_map_ego_centric followed by the image part of augment_bev (utils.py:508-511) on the 9 map channels, per-frame
+ * parameters as in bevgen_augment (device copy + host copy): frames that neither rotate nor scale get flip / dropout
+ * fused into the bit-plane expand; the others are resampled straight from the bit planes (no intermediate float grid).
+ * Same bits as bevgen_map_raster followed by bevgen_augment. */
+int bevgen_map_raster_augmented(const double *verts, const int32_t *pl_off, const int32_t *lanes,
+                                const int32_t *cws, const int32_t *frame_map, const double *ego_T,
+                                int B, int max_prims, int max_polyline_verts,
+                                const bevgen_aug_params *params, const bevgen_aug_params *params_host,
+                                float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

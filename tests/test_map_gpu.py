@@ -127,3 +127,28 @@ def test_reference_signature_and_error_conventions(bg, co, tmp_path, capsys):
     # empty map dict
     p2 = tmp_path / "empty.json"; p2.write_text(json.dumps({}))
     assert not bg.rasterize_map_ego_centric(str(p2), f.pose_series()).any()
+
+
+def test_augmented_maps_from_bit_planes_match_raster_then_augment_and_oracle(bg, co):
+    """bevgen_map_raster_augmented: the 9 map channels resampled straight from the rasterizer's bit planes == rasterize,
+    then the dense augmentation kernel == the oracle's flip -> rotate -> scale -> dropout of the oracle's map"""
+    md = bg.synthetic.synthetic_map(seed=21, rows=8, cols=7, n_cross=5)
+    table = bg.MapTable([bg.maps.parse_map_dict(md)])
+    poses = _poses(6, 5)
+    Ts = np.stack([bg.pose.map_matrix_from_pose(tx, ty, q) for tx, ty, q in poses])
+    ps = [bg.AugParams(), bg.AugParams(flip=True, rects=[(30, 40, 50, 45)]), bg.AugParams(angle_deg=-14.0, flip=True),
+          bg.AugParams(scale=0.951, rects=[(0, 0, 25, 25), (370, 680, 30, 40)]), bg.AugParams(angle_deg=9.5, scale=1.049),
+          bg.AugParams(angle_deg=3.0, scale=0.97, flip=True, rects=[(100, 100, 50, 50)])]
+    got = bg.map_ops.rasterize_maps_augmented(table, [0] * 6, Ts, ps)
+    dense = bg.augment_grid(bg.rasterize_maps(table, [0] * 6, Ts), ps)
+    assert torch.equal(got, dense)
+    flat = co.flatten_map(md)
+    got = got.cpu().numpy()
+    for b, p in enumerate(ps):
+        g = co.map_raster_flat(flat, Ts[b])
+        if p.flip: g = co.flip_w(g)
+        if p.angle_deg is not None: g = co.rotate(g, p.angle_deg)
+        if p.scale is not None: g = co.scale(g, p.scale)
+        g = np.ascontiguousarray(g).copy()
+        if p.rects: co.dropout(g, p.rects)
+        assert np.array_equal(got[b], g), (b, p)

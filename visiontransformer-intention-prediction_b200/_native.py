@@ -73,6 +73,7 @@ PROTOTYPES = {
     "bevgen_map_raster": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "bevgen_world_to_bev_pixel": (_i, [_p, _i64, _p, _p, _p]),
     "bevgen_augment": (_i, [_p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "bevgen_map_raster_augmented": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "bevgen_aug_fused_supported": (_i, [_p, _i]),
     "bevgen_lidar_aug_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
     "bevgen_lidar_bev_augmented": (_i, [_p, _i, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),

@@ -29,7 +29,24 @@ struct RotTap {                                  // 4 taps of cv2's remapBilinea
 
 __device__ __forceinline__ int flip_x(int x, bool flip) { return flip ? kW - 1 - x : x; }
 
+// Source of the gather: a float32 grid, or the map rasterizer's bit planes (values 0 / 1; an "offset" is then a bit index
+// in the 768-bit-row layout) -- same arithmetic downstream, no intermediate float grid for the map channels.
+template <bool BITS> struct AugSrc;
+template <> struct AugSrc<false> {
+    using T = float;
+    static constexpr int kRow = kW, kPlaneElems = kPlane;
+    static __device__ __forceinline__ float ld(const float* __restrict__ plane, int off) { return __ldg(plane + off); }
+};
+template <> struct AugSrc<true> {
+    using T = uint32_t;
+    static constexpr int kRow = kMapWordsPerRow * 32, kPlaneElems = kMapPlaneWords;
+    static __device__ __forceinline__ float ld(const uint32_t* __restrict__ plane, int off) {
+        return ((__ldg(plane + (off >> 5)) >> (off & 31)) & 1u) ? 1.0f : 0.0f;
+    }
+};
+
 // cv2.warpAffine coordinate scheme (aug_geom.cuh)
+template <int ROWSTRIDE>
 __device__ __forceinline__ RotTap rot_taps(const double* __restrict__ M, int y, int x, bool flip) {
     const int X = (rot_X0(M, y) + rot_adelta(M, x)) >> 5, Y = (rot_Y0(M, y) + rot_bdelta(M, x)) >> 5;
     int sx = X >> 5, sy = Y >> 5;
@@ -39,16 +56,17 @@ __device__ __forceinline__ RotTap rot_taps(const double* __restrict__ M, int y, 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int xx = sx + (k & 1), yy = sy + (k >> 1);
-        t.off[k] = (xx >= 0 && xx < kW && yy >= 0 && yy < kH) ? yy * kW + flip_x(xx, flip) : -1;
+        t.off[k] = (xx >= 0 && xx < kW && yy >= 0 && yy < kH) ? yy * ROWSTRIDE + flip_x(xx, flip) : -1;
     }
     return t;
 }
 
-__device__ __forceinline__ float rot_eval(const float* __restrict__ plane, const RotTap& t) {
-    const float v0 = t.off[0] >= 0 ? __ldg(plane + t.off[0]) : 0.f;
-    const float v1 = t.off[1] >= 0 ? __ldg(plane + t.off[1]) : 0.f;
-    const float v2 = t.off[2] >= 0 ? __ldg(plane + t.off[2]) : 0.f;
-    const float v3 = t.off[3] >= 0 ? __ldg(plane + t.off[3]) : 0.f;
+template <bool BITS>
+__device__ __forceinline__ float rot_eval(const typename AugSrc<BITS>::T* __restrict__ plane, const RotTap& t) {
+    const float v0 = t.off[0] >= 0 ? AugSrc<BITS>::ld(plane, t.off[0]) : 0.f;
+    const float v1 = t.off[1] >= 0 ? AugSrc<BITS>::ld(plane, t.off[1]) : 0.f;
+    const float v2 = t.off[2] >= 0 ? AugSrc<BITS>::ld(plane, t.off[2]) : 0.f;
+    const float v3 = t.off[3] >= 0 ? AugSrc<BITS>::ld(plane, t.off[3]) : 0.f;
     return rot_sum(v0, v1, v2, v3, t.w);
 }
 
@@ -60,9 +78,11 @@ struct FrameList {                               // frames of one class, passed 
 
 // One thread per output pixel (x fastest), looping over the C channels of its frame.  ROT / SCL are uniform per
 // launch (the host groups frames by class), so the channel loop carries no dead code: 1, 4, 4 or 16 taps per value.
-template <bool ROT, bool SCL>
-__global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict__ src, float* __restrict__ dst, int C,
+template <bool ROT, bool SCL, bool BITS>
+__global__ void __launch_bounds__(kAugThreads) k_augment(const typename AugSrc<BITS>::T* __restrict__ src, float* __restrict__ dst, int C,
                                                          const bevgen_aug_params* __restrict__ params, FrameList fl) {
+    using Src = AugSrc<BITS>;
+    using SrcT = typename Src::T;
     const int x = blockIdx.x * kAugThreads + threadIdx.x, y = blockIdx.y;
     const int bsrc = fl.src[blockIdx.z], bdst = fl.dst[blockIdx.z];
     __shared__ bevgen_aug_params P;
@@ -99,7 +119,7 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
         if (NQ == 4) { qy[1] = sy0; qx[1] = sx1; qy[2] = sy1; qx[2] = sx0; qy[3] = sy1; qx[3] = sx1; }
     }
     const size_t pix = (size_t)y * kW + x;
-    const float* sp = src + (size_t)bsrc * C * kPlane;
+    const SrcT* sp = src + (size_t)bsrc * C * Src::kPlaneElems;
     float* dp = dst + (size_t)bdst * C * kPlane + pix;
     if (dropped || outside) {
 #pragma unroll 8
@@ -110,8 +130,8 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
     int direct[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-        direct[q] = qy[q] * kW + flip_x(qx[q], flip);
-        if (ROT) tap[q] = rot_taps(P.minv, qy[q], qx[q], flip);
+        direct[q] = qy[q] * Src::kRow + flip_x(qx[q], flip);
+        if (ROT) tap[q] = rot_taps<Src::kRow>(P.minv, qy[q], qx[q], flip);
     }
 
     // ---- channel loop: U channels per iteration, all loads issued before the first use ------------------
@@ -125,14 +145,14 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
         float v[U][NQ][ROT ? 4 : 1];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float* plane = sp + (size_t)(c + u) * kPlane;
+            const SrcT* plane = sp + (size_t)(c + u) * Src::kPlaneElems;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 if (ROT) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) v[u][q][k] = tap[q].off[k] >= 0 ? __ldg(plane + tap[q].off[k]) : 0.f;
+                    for (int k = 0; k < 4; ++k) v[u][q][k] = tap[q].off[k] >= 0 ? Src::ld(plane, tap[q].off[k]) : 0.f;
                 } else {
-                    v[u][q][0] = __ldg(plane + direct[q]);
+                    v[u][q][0] = Src::ld(plane, direct[q]);
                 }
             }
         }
@@ -151,16 +171,48 @@ __global__ void __launch_bounds__(kAugThreads) k_augment(const float* __restrict
         }
     }
     for (; c < C; ++c) {
-        const float* plane = sp + (size_t)c * kPlane;
+        const SrcT* plane = sp + (size_t)c * Src::kPlaneElems;
         float r[NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) r[q] = ROT ? rot_eval(plane, tap[q]) : __ldg(plane + direct[q]);
+        for (int q = 0; q < NQ; ++q) r[q] = ROT ? rot_eval<BITS>(plane, tap[q]) : Src::ld(plane, direct[q]);
         __stcs(dp + (size_t)c * kPlane, value(r));
     }
 }
 
 }  // namespace
 }  // namespace bevgen
+
+// map bit planes -> augmented float32 map grids for the frames that rotate / scale (one fused gather per class; the
+// 16-tap form for rotate + scale: 9 channels of 0 / 1 values need no scratch pass)
+int bevgen::launch_augment_bitplanes(const uint32_t* planes, float* dst, int B, const bevgen_aug_params* params,
+                                     const bevgen_aug_params* params_host, cudaStream_t st) {
+    if (B <= 0 || !planes || !dst || !params || !params_host) return BEVGEN_E_INVALID_ARG;
+    if (B > 32767) return BEVGEN_E_UNSUPPORTED;
+    for (int cls = 1; cls < 4; ++cls) {
+        FrameList fl;
+        fl.n = 0; fl.use_flip = 1; fl.use_rects = 1;
+        auto flush = [&]() -> int {
+            if (fl.n == 0) return 0;
+            const dim3 grid(kW / kAugThreads, kH, fl.n);
+            switch (cls) {
+                case 1:  BEVGEN_LAUNCH("k_augment", st, k_augment<true, false, true><<<grid, kAugThreads, 0, st>>>(planes, dst, kMapC, params, fl)); break;
+                case 2:  BEVGEN_LAUNCH("k_augment", st, k_augment<false, true, true><<<grid, kAugThreads, 0, st>>>(planes, dst, kMapC, params, fl)); break;
+                default: BEVGEN_LAUNCH("k_augment", st, k_augment<true, true, true><<<grid, kAugThreads, 0, st>>>(planes, dst, kMapC, params, fl)); break;
+            }
+            fl.n = 0;
+            return 0;
+        };
+        for (int b = 0; b < B; ++b) {
+            if (((params_host[b].do_rotate != 0) | ((params_host[b].do_scale != 0) << 1)) == cls) {
+                fl.src[fl.n] = fl.dst[fl.n] = fl.par[fl.n] = (short)b;
+                if (++fl.n == 60) { const int rc = flush(); if (rc) return rc; }
+            }
+        }
+        const int rc = flush();
+        if (rc) return rc;
+    }
+    return 0;
+}
 
 using namespace bevgen;
 
@@ -178,10 +230,10 @@ extern "C" int bevgen_augment(const float* src, float* dst, int B, int C, const 
     auto launch = [&](int cls, const float* s, float* d, const FrameList& fl) -> int {
         const dim3 grid(kW / kAugThreads, kH, fl.n);
         switch (cls) {
-            case 3:  BEVGEN_LAUNCH("k_augment", st, k_augment<true, true><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
-            case 1:  BEVGEN_LAUNCH("k_augment", st, k_augment<true, false><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
-            case 2:  BEVGEN_LAUNCH("k_augment", st, k_augment<false, true><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
-            default: BEVGEN_LAUNCH("k_augment", st, k_augment<false, false><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
+            case 3:  BEVGEN_LAUNCH("k_augment", st, k_augment<true, true, false><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
+            case 1:  BEVGEN_LAUNCH("k_augment", st, k_augment<true, false, false><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
+            case 2:  BEVGEN_LAUNCH("k_augment", st, k_augment<false, true, false><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
+            default: BEVGEN_LAUNCH("k_augment", st, k_augment<false, false, false><<<grid, kAugThreads, 0, st>>>(s, d, C, params, fl)); break;
         }
         return 0;
     };

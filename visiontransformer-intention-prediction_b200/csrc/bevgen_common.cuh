@@ -22,6 +22,10 @@ constexpr double kZSpan = kZMax - kZMin;   // folded in IEEE double exactly like
 constexpr int kPlane = kH * kW;            // 288 000
 constexpr int kMaxRects = BEVGEN_MAX_DROP_RECTS;
 
+// map bit planes (map_raster.cu): 768-bit rows, one plane per channel
+constexpr int kMapWordsPerRow = 24;                    // 768 bits >= 720 columns
+constexpr int kMapPlaneWords = kH * kMapWordsPerRow;   // 9 600 u32 per channel
+
 extern long long g_launch_count;           // host-side counter (cabi.cu)
 
 #define BEVGEN_CHECK_LAUNCH()                                  \
@@ -30,6 +34,11 @@ extern long long g_launch_count;           // host-side counter (cabi.cu)
         cudaError_t e__ = cudaGetLastError();                  \
         if (e__ != cudaSuccess) return (int)e__;               \
     } while (0)
+
+// augmentation of map BIT PLANES straight into float32 grids (augment.cu; used by bevgen_map_raster_augmented):
+// frames b with do_rotate / do_scale in params_host: planes [B,9,400,24] u32 -> dst [B,9,400,720]
+int launch_augment_bitplanes(const uint32_t* planes, float* dst, int B, const bevgen_aug_params* params,
+                             const bevgen_aug_params* params_host, cudaStream_t st);
 
 // optional per-kernel timing (bench.py): CUDA events recorded on the launching stream around each launch
 void timing_begin(const char* name, cudaStream_t st);

@@ -17,8 +17,8 @@
 namespace bevgen {
 namespace {
 
-constexpr int kWordsPerRow = 24;                       // 768 bits >= 720 columns
-constexpr int kPlaneWords = kH * kWordsPerRow;         // 9 600 u32 per channel
+constexpr int kWordsPerRow = kMapWordsPerRow;          // 768 bits >= 720 columns
+constexpr int kPlaneWords = kMapPlaneWords;            // 9 600 u32 per channel
 constexpr int kFrameWords = kMapC * kPlaneWords;       // 86 400 u32 = 345 600 B per frame
 constexpr int kDrawWarps = 4;
 constexpr int kDrawThreads = kDrawWarps * 32;
@@ -264,9 +264,11 @@ __global__ void __launch_bounds__(kDrawThreads) k_map_draw(MapIn in, uint32_t* _
 constexpr int kExpRows = 10;
 constexpr int kExpBytes = kExpRows * kW * 4;            // 28 800
 constexpr int kExpBands = kH / kExpRows;                // 40
+// With `aug` (bevgen_map_raster_augmented) flip / rectangles come from the frame's parameters, and frames that rotate or
+// scale are left to the bit-plane gather (augment.cu).
 __global__ void __launch_bounds__(128) k_map_expand(const uint32_t* __restrict__ bitplanes, float* __restrict__ out,
                                                     const uint8_t* __restrict__ flip, const int32_t* __restrict__ rects,
-                                                    const int32_t* __restrict__ nrects) {
+                                                    const int32_t* __restrict__ nrects, const bevgen_aug_params* __restrict__ aug) {
     extern __shared__ __align__(128) unsigned char mtile[];
     __shared__ uint32_t words[kExpRows * kWordsPerRow];
     __shared__ int sRect[kMaxRects * 4];
@@ -276,10 +278,18 @@ __global__ void __launch_bounds__(128) k_map_expand(const uint32_t* __restrict__
     const int y0 = (int)band * kExpRows;
     const uint32_t* src = bitplanes + (size_t)bc * kPlaneWords + y0 * kWordsPerRow;
     for (int i = tid; i < kExpRows * kWordsPerRow; i += 128) words[i] = __ldg(src + i);
-    const bool fl = flip ? (flip[b] != 0) : false;
+    bool fl = flip ? (flip[b] != 0) : false;
     int nr = nrects ? nrects[b] : 0;
+    const int32_t* rsrc = rects ? rects + (size_t)b * kMaxRects * 4 : nullptr;
+    if (aug) {
+        const bevgen_aug_params* P = aug + b;
+        if (P->do_rotate | P->do_scale) return;         // whole CTA
+        fl = P->do_flip != 0;
+        nr = P->n_rects < 0 ? 0 : P->n_rects;
+        rsrc = P->rects;
+    }
     nr = nr > kMaxRects ? kMaxRects : nr;
-    if (tid < 4 * nr) sRect[tid] = rects[(size_t)b * kMaxRects * 4 + tid];
+    if (tid < 4 * nr) sRect[tid] = rsrc[tid];
     __syncthreads();
     constexpr int kRow4 = kW / 4;                       // 180 float4 per row
     for (int i = tid; i < kExpRows * kRow4; i += 128) {
@@ -322,17 +332,10 @@ extern "C" size_t bevgen_map_workspace_bytes(int B) {
     return B > 0 ? (size_t)B * kFrameWords * sizeof(uint32_t) : 0;
 }
 
-extern "C" int bevgen_map_raster(const double* verts, const int32_t* pl_off, const int32_t* lanes, const int32_t* cws,
-                                 const int32_t* frame_map, const double* ego_T, int B, int max_prims, int max_polyline_verts,
-                                 const uint8_t* flip,
-                                 const int32_t* drop_rects, const int32_t* drop_counts, float* out, void* workspace,
-                                 size_t workspace_bytes, bevgen_stream_t stream) {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (B <= 0 || max_prims < 0 || !out || !frame_map || !ego_T) return BEVGEN_E_INVALID_ARG;
-    if ((drop_rects == nullptr) != (drop_counts == nullptr)) return BEVGEN_E_INVALID_ARG;
-    if (!workspace || workspace_bytes < bevgen_map_workspace_bytes(B)) return BEVGEN_E_WORKSPACE;
-    if (B > 65535) return BEVGEN_E_UNSUPPORTED;
-    uint32_t* planes = static_cast<uint32_t*>(workspace);
+namespace {
+// clear the bit planes and draw every frame's primitives into them
+int draw_maps(const double* verts, const int32_t* pl_off, const int32_t* lanes, const int32_t* cws, const int32_t* frame_map,
+              const double* ego_T, int B, int max_prims, int max_polyline_verts, uint32_t* planes, cudaStream_t st) {
     BEVGEN_CUDA(cudaMemsetAsync(planes, 0, bevgen_map_workspace_bytes(B), st));
     if (max_prims > 0) {
         if (!verts || !pl_off) return BEVGEN_E_INVALID_ARG;
@@ -348,10 +351,52 @@ extern "C" int bevgen_map_raster(const double* verts, const int32_t* pl_off, con
         const dim3 grid((max_prims + kDrawWarps - 1) / kDrawWarps, B);
         BEVGEN_LAUNCH("k_map_draw", st, k_map_draw<<<grid, kDrawThreads, smem, st>>>(in, planes, maxv));
     }
-    if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;      // TMA bulk stores need 16 B alignment
-    BEVGEN_LAUNCH("k_map_expand", st,
-                  k_map_expand<<<(unsigned)(B * kMapC * kExpBands), 128, kExpBytes, st>>>(planes, out, flip, drop_rects, drop_counts));
     return 0;
+}
+}  // namespace
+
+extern "C" int bevgen_map_raster(const double* verts, const int32_t* pl_off, const int32_t* lanes, const int32_t* cws,
+                                 const int32_t* frame_map, const double* ego_T, int B, int max_prims, int max_polyline_verts,
+                                 const uint8_t* flip,
+                                 const int32_t* drop_rects, const int32_t* drop_counts, float* out, void* workspace,
+                                 size_t workspace_bytes, bevgen_stream_t stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B <= 0 || max_prims < 0 || !out || !frame_map || !ego_T) return BEVGEN_E_INVALID_ARG;
+    if ((drop_rects == nullptr) != (drop_counts == nullptr)) return BEVGEN_E_INVALID_ARG;
+    if (!workspace || workspace_bytes < bevgen_map_workspace_bytes(B)) return BEVGEN_E_WORKSPACE;
+    if (B > 65535) return BEVGEN_E_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;      // TMA bulk stores need 16 B alignment
+    uint32_t* planes = static_cast<uint32_t*>(workspace);
+    const int rc = draw_maps(verts, pl_off, lanes, cws, frame_map, ego_T, B, max_prims, max_polyline_verts, planes, st);
+    if (rc) return rc;
+    BEVGEN_LAUNCH("k_map_expand", st,
+                  k_map_expand<<<(unsigned)(B * kMapC * kExpBands), 128, kExpBytes, st>>>(planes, out, flip, drop_rects, drop_counts, nullptr));
+    return 0;
+}
+
+extern "C" int bevgen_map_raster_augmented(const double* verts, const int32_t* pl_off, const int32_t* lanes, const int32_t* cws,
+                                           const int32_t* frame_map, const double* ego_T, int B, int max_prims,
+                                           int max_polyline_verts, const bevgen_aug_params* params,
+                                           const bevgen_aug_params* params_host, float* out, void* workspace,
+                                           size_t workspace_bytes, bevgen_stream_t stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B <= 0 || max_prims < 0 || !out || !frame_map || !ego_T || !params || !params_host) return BEVGEN_E_INVALID_ARG;
+    if (!workspace || workspace_bytes < bevgen_map_workspace_bytes(B)) return BEVGEN_E_WORKSPACE;
+    if (B > 32767) return BEVGEN_E_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
+    uint32_t* planes = static_cast<uint32_t*>(workspace);
+    int rc = draw_maps(verts, pl_off, lanes, cws, frame_map, ego_T, B, max_prims, max_polyline_verts, planes, st);
+    if (rc) return rc;
+    bool any_plain = false, any_resampled = false;
+    for (int b = 0; b < B; ++b) {
+        const bool r = params_host[b].do_rotate != 0 || params_host[b].do_scale != 0;
+        any_resampled |= r; any_plain |= !r;
+    }
+    if (any_plain)      // frames that neither rotate nor scale: flip / dropout fused into the expand; the others' CTAs exit at once
+        BEVGEN_LAUNCH("k_map_expand", st,
+                      k_map_expand<<<(unsigned)(B * kMapC * kExpBands), 128, kExpBytes, st>>>(planes, out, nullptr, nullptr, nullptr, params));
+    if (any_resampled) rc = launch_augment_bitplanes(planes, out, B, params, params_host, st);
+    return rc;
 }
 
 extern "C" int bevgen_world_to_bev_pixel(const double* xy, int64_t m, const double* T_host, int64_t* out,

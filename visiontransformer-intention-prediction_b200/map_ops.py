@@ -83,6 +83,39 @@ def rasterize_maps(table: MapTable, map_ids, ego_T, *, flip=None, drop_rects=Non
     return out
 
 
+def rasterize_maps_augmented(table: MapTable, map_ids, ego_T, params, *, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils.py:108-182 followed by the image part of augment_bev (utils.py:508-511) on the 9 map channels, for a batch:
+    ``params`` = one ``augment.AugParams`` per frame.  Frames that rotate / scale are resampled straight from the
+    rasterizer's bit planes (no intermediate float grid); the others get flip / dropout fused into the expand."""
+    import ctypes as C
+    from . import augment as _aug
+    device = table.device
+    ids = np.asarray(map_ids, np.int64).reshape(-1)
+    B = ids.shape[0]
+    if len(params) != B:
+        raise ValueError("one AugParams per frame")
+    rows = table.frame_rows[ids]
+    T = _dev(np.asarray(ego_T, np.float64).reshape(B, 9) if not isinstance(ego_T, torch.Tensor) else ego_T,
+             torch.float64, device).reshape(B, 9)
+    fmap = _dev(rows, torch.int32, device)
+    max_prims = int((rows[:, 1] + rows[:, 3]).max()) if B else 0
+    shape = (B, MAP_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
+    hparams = _aug.pack_params(params)
+    dparams = _dev(hparams, torch.uint8, device)
+    L = _native.lib()
+    wbytes = int(L.bevgen_map_workspace_bytes(B))
+    ws = workspace.get("map", wbytes, device)
+    rc = L.bevgen_map_raster_augmented(_ptr(table.verts), _ptr(table.pl_off), _ptr(table.lanes), _ptr(table.cws), _ptr(fmap),
+                                       _ptr(T), B, max_prims, int(table.max_polyline_len), _ptr(dparams),
+                                       C.c_void_p(hparams.ctypes.data), _ptr(out), _ptr(ws), wbytes, _stream_ptr())
+    _native.check(rc, "bevgen_map_raster_augmented")
+    return out
+
+
 _TABLES: Dict[str, MapTable] = {}
 
 

@@ -178,21 +178,9 @@ class BevGenerator:
             _aug.lidar_bev_augmented(dv["points4"], dv["sweep_offsets"], dv["rel_tf"], B, S, aug,
                                      max_sweep_points=batch.max_sweep_points, out=out_lidar)
             if with_map:
-                # map: 3 % of the bytes -- dense route (raster into scratch, gather) for the frames that resample
+                # map channels: resampled straight from the rasterizer's bit planes, on the side stream
                 with torch.cuda.stream(self._map_stream):
-                    need_idx = [i for i, nd in enumerate(need) if nd]
-                    lo, hi = need_idx[0], need_idx[-1] + 1          # contiguous [0, J) when partitioned
-                    gen_m = self._buf("gen_m", (hi - lo,) + mshape[1:])
-                    sl = slice(lo, hi)
-                    map_ops.rasterize_maps(self.map_table, ids[sl], d_T[sl], flip=d_flip[sl], drop_rects=d_rects[sl],
-                                           drop_counts=d_cnt[sl], out=gen_m)
-                    gp = [p if p.needs_gather else _aug.AugParams() for p in aug[lo:hi]]
-                    _aug.augment_grid(gen_m, gp, out=out_map[sl])
-                    for a, b in ((0, lo), (hi, B)):
-                        if b > a:
-                            s2 = slice(a, b)
-                            map_ops.rasterize_maps(self.map_table, ids[s2], d_T[s2], flip=d_flip[s2], drop_rects=d_rects[s2],
-                                                   drop_counts=d_cnt[s2], out=out_map[s2])
+                    map_ops.rasterize_maps_augmented(self.map_table, ids, d_T, aug, out=out_map)
         elif J == 0:
             run(0, B, out_lidar, out_map)
         else:
