@@ -373,8 +373,8 @@ def run_ours(args) -> None:
     }
     n_gather = sum(1 for p in (aug or []) if p.needs_gather)
     fused_aug = bool(aug) and "k_tile_aug" in kernels
-    if fused_aug:       # the gather then only covers the map grids of the resampled frames
-        own_bytes["k_augment"] = 2 * MAP_FRAME_BYTES
+    if fused_aug:       # the gather then only writes the map grids of the resampled frames (source: L2-resident bit planes)
+        own_bytes["k_augment"] = MAP_FRAME_BYTES
     peak = FALLBACK_HBM_GBS
     peak_src = "fallback"
     mp_path = ROOT / "MEASURED_PEAKS.json"
