@@ -13,14 +13,16 @@
 //   k_rebin_aug   the row-band record bins of k_bin_fixed -> one bin per (sweep, height channel, output tile) holding the
 //                 records inside that tile's footprint (a record lands in 1-4 tiles), including the channel's records in
 //                 the sweep's overflow list.  One CTA per (frame, sweep, channel) is the only writer of its 100 bins:
-//                 slots come from shared-memory counters, no global atomics.
+//                 slots come from shared-memory counters, no global atomics.  A record is stored as the tile kernel's
+//                 work-list entry: position inside the footprint + origin of the rotation's candidate window.
 //   k_tile_aug    one CTA per (frame, sweep, output tile) walks the sweep's 29 height channels:
-//     A  the tile's records of the channel (fetched one channel ahead with cp.async) -> max into a shared-memory copy T0
+//     A  the tile's records of the channel (fetched two channels ahead with cp.async) -> max into a shared-memory copy T0
 //        of the footprint (the mirrored column of a flipped frame is already in the record)
 //     B  rotation: for every (record, one of 3 x 3 candidate destination pixels around the forward-mapped voxel) pair, in
 //        parallel over the CTA: if the pixel's cv2 fixed-point tap set really contains the voxel it is evaluated from T0
 //        with the reference's exact arithmetic (aug_geom.cuh).  Resize: the taps are separable and monotone, so an inverse
-//        tap table gives exactly the output rows / columns a source pixel feeds.  Results go into the shared output tile O;
+//        tap table gives exactly the output rows / columns a source pixel feeds (work items: 3 rows per record for
+//        scale-only frames, 2 x 2 pixels per listed pixel after a rotation).  Results go into the shared output tile O;
 //        rotate + scale goes through an intermediate tile T1 (the rotated image's float32 rounding is part of the
 //        reference's result) whose non-zero pixels are listed as they are produced.
 //     C  O -> HBM (40 row pieces of 288 B, 16-byte stores; measured faster here than 40 small bulk copies), then only the
