@@ -406,7 +406,9 @@ def run_ours(args) -> None:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_step / per_step,
-                    "ms_per_launch": k["ms_per_step"] / per_step}
+                    "ms_per_launch": k["ms_per_step"] / per_step,
+                    "peak_note": "peak = measured copy bandwidth (read + write); a write-only stream can exceed it "
+                                 "(zero-fill alone: 7.5 TB/s, profiles/r1_fillbench.txt)"}
     step_gbs = fbytes * B / (total_ms_plain / K / 1e3) / 1e9
 
     e2e_value = frames_total / (e2e_ms / 1e3)
