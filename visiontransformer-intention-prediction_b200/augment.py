@@ -149,16 +149,16 @@ def augment_grid(src: torch.Tensor, params: Sequence[AugParams], out: Optional[t
     return out
 
 
-def fused_supported(params: Sequence[AugParams]) -> bool:
+def fused_supported(params: Sequence[AugParams], packed: Optional[np.ndarray] = None) -> bool:
     """True when every frame's parameters fit the fused generation+augmentation tile kernel (always true for the
-    reference's own draws: |angle| <= 15 deg, 0.95 <= scale <= 1.05)."""
-    hp = pack_params(params)
+    reference's own draws: |angle| <= 15 deg, 0.95 <= scale <= 1.05).  ``packed`` = pack_params(params) if at hand."""
+    hp = pack_params(params) if packed is None else packed
     return bool(_native.lib().bevgen_aug_fused_supported(C.c_void_p(hp.ctypes.data), len(params)))
 
 
 def lidar_bev_augmented(points4: torch.Tensor, sweep_offsets: torch.Tensor, rel_tf: torch.Tensor, num_frames: int,
                         num_sweeps: int, params: Sequence[AugParams], *, max_sweep_points: int,
-                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        out: Optional[torch.Tensor] = None, packed: Optional[np.ndarray] = None) -> torch.Tensor:
     """create_intentnet_lidar_bev (utils.py:62-106) + the image part of augment_bev (utils.py:508-511) for a batch, every
     output byte written once: frames that rotate / scale are built directly in augmented form from the binned point
     records (csrc/lidar_aug_tile.cuh) instead of generate -> read back -> resample -> write.  Device tensors in
@@ -180,7 +180,7 @@ def lidar_bev_augmented(points4: torch.Tensor, sweep_offsets: torch.Tensor, rel_
         out = torch.empty(shape, dtype=torch.float32, device=device)
     elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
         raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
-    hparams = pack_params(params)
+    hparams = pack_params(params) if packed is None else packed
     dparams = _dev(hparams, torch.uint8, device)
     L = _native.lib()
     n = int(pts.shape[0])

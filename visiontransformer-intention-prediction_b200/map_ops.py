@@ -83,7 +83,8 @@ def rasterize_maps(table: MapTable, map_ids, ego_T, *, flip=None, drop_rects=Non
     return out
 
 
-def rasterize_maps_augmented(table: MapTable, map_ids, ego_T, params, *, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def rasterize_maps_augmented(table: MapTable, map_ids, ego_T, params, *, out: Optional[torch.Tensor] = None,
+                             packed: Optional[np.ndarray] = None) -> torch.Tensor:
     """utils.py:108-182 followed by the image part of augment_bev (utils.py:508-511) on the 9 map channels, for a batch:
     ``params`` = one ``augment.AugParams`` per frame.  Frames that rotate / scale are resampled straight from the
     rasterizer's bit planes (no intermediate float grid); the others get flip / dropout fused into the expand."""
@@ -104,7 +105,7 @@ def rasterize_maps_augmented(table: MapTable, map_ids, ego_T, params, *, out: Op
         out = torch.empty(shape, dtype=torch.float32, device=device)
     elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
-    hparams = _aug.pack_params(params)
+    hparams = _aug.pack_params(params) if packed is None else packed
     dparams = _dev(hparams, torch.uint8, device)
     L = _native.lib()
     wbytes = int(L.bevgen_map_workspace_bytes(B))

@@ -128,20 +128,28 @@ class BevGenerator:
                  with_map: bool = True, out_lidar: Optional[torch.Tensor] = None,
                  out_map: Optional[torch.Tensor] = None) -> dict:
         """Returns {"lidar_bev", "map_bev"} CUDA tensors.  ``aug`` = one AugParams per frame (train time):
-        flip / dropout of frames that need no resampling are fused into generation (zero extra bytes); if any
-        frame rotates or scales, the batch goes through the single fused gather kernel."""
+        flip / dropout of frames that need no resampling are fused into generation (zero extra bytes); frames that
+        rotate or scale are built directly in augmented form (LiDAR from the binned point records, map channels from
+        the rasterizer's bit planes) -- or, with ``fused_augment=False`` / parameters outside the fused kernel's reach,
+        generated into scratch and resampled by the dense gather kernel.  Same bits either way."""
         B, S = batch.num_frames, batch.num_sweeps
         dv = dev if dev is not None else self.upload(batch)
         flip = rects = cnt = None
-        J = 0                                   # frames [0, J) go through the gather kernel
+        J = 0                                   # dense route: frames [0, J) go through the gather kernel
+        packed = None                           # fused route: the packed per-frame parameters
         if aug is not None:
             if len(aug) != B:
                 raise ValueError("one AugParams per frame")
-            flip, rects, cnt = _aug.fusion_arrays(aug)
             need = [p.needs_gather for p in aug]
             J = sum(need)
-            if J and not all(need[:J]):
-                J = B                           # not partitioned (partition_for_augmentation): gather the whole batch
+            if J and self.fused_augment and self.algo == bev_ops.ALGO_TILED:
+                packed = _aug.pack_params(aug)
+                if not _aug.fused_supported(aug, packed):
+                    packed = None               # parameters outside the fused kernel's reach: dense route
+            if packed is None:
+                flip, rects, cnt = _aug.fusion_arrays(aug)
+                if J and not all(need[:J]):
+                    J = B                       # not partitioned (partition_for_augmentation): gather the whole batch
         lshape = (B, S * LIDAR_HEIGHT_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
         mshape = (B, MAP_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
         if with_map and (self.map_table is None or (batch.map_ids < 0).any()):
@@ -173,14 +181,14 @@ class BevGenerator:
         main = torch.cuda.current_stream()
         if with_map:
             self._map_stream.wait_stream(main)          # inputs (uploads, fusion arrays) are ready on the main stream
-        if J and self.fused_augment and self.algo == bev_ops.ALGO_TILED and _aug.fused_supported(aug):
+        if packed is not None:
             # LiDAR: one pass for the whole batch, whatever the frame order (no partition needed)
             _aug.lidar_bev_augmented(dv["points4"], dv["sweep_offsets"], dv["rel_tf"], B, S, aug,
-                                     max_sweep_points=batch.max_sweep_points, out=out_lidar)
+                                     max_sweep_points=batch.max_sweep_points, out=out_lidar, packed=packed)
             if with_map:
                 # map channels: resampled straight from the rasterizer's bit planes, on the side stream
                 with torch.cuda.stream(self._map_stream):
-                    map_ops.rasterize_maps_augmented(self.map_table, ids, d_T, aug, out=out_map)
+                    map_ops.rasterize_maps_augmented(self.map_table, ids, d_T, aug, out=out_map, packed=packed)
         elif J == 0:
             run(0, B, out_lidar, out_map)
         else:
