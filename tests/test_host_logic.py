@@ -134,3 +134,35 @@ def test_pinned_pool_never_aliases_live_results(monkeypatch):
     assert pool._idle_bytes == t.numel() * 4       # now it is back
     c = pool.to_numpy(t * 2)
     assert c.ctypes.data == ptr and c[3] == 6 and b[5] == 6               # recycled; the live result is untouched
+
+
+def test_offset_validation(bg):
+    """Host-side CSR checks: offsets must be ordered and inside the point array; max_sweep_points is a sizing
+    hint that is corrected upward, never trusted below the largest sweep."""
+    from bevgen_b200.bev_ops import _check_offsets
+    assert _check_offsets(np.array([0, 5, 5, 12]), 12, None) == 7
+    assert _check_offsets(np.array([0, 5, 5, 12]), 12, 3) == 7          # too small a hint is corrected
+    assert _check_offsets(np.array([0, 5, 5, 12]), 12, 100) == 100
+    assert _check_offsets(np.zeros(0), 0, None) == 0
+    for bad in ([0, 6, 5, 12], [-1, 5, 12], [0, 5, 13]):
+        with pytest.raises(ValueError):
+            _check_offsets(np.array(bad), 12, None)
+
+
+def test_sweep_cache_is_byte_bounded():
+    from bevgen_b200.sweep_io import _SweepCache
+    c = _SweepCache(max_bytes=10 * 1024)
+    blk = lambda: np.zeros((512, 4), np.float16)      # 4 KiB + overhead
+    c.put("a", blk()); c.put("b", blk())
+    assert len(c) == 2 and c.nbytes <= c.max_bytes
+    assert c.get("a")[0]                               # touch a -> b is now the eviction candidate
+    c.put("c", blk())
+    assert len(c) == 2 and c.get("a")[0] and c.get("c")[0] and not c.get("b")[0]
+    c.put("none", None)                                # "missing sweep" results are cached too (tiny)
+    assert c.get("none") == (True, None)
+    c.put("huge", np.zeros((4096, 4), np.float32))     # larger than the whole budget: not cached, nothing evicted for it
+    assert not c.get("huge")[0] and c.nbytes <= c.max_bytes
+    c.resize(0)
+    assert len(c) == 0 and c.nbytes == 0
+    c.put("a", blk())
+    assert len(c) == 0

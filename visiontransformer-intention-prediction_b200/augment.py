@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .bev_ops import _dev, _ptr, _require_cuda, _stream_ptr, to_numpy_fresh, workspace
+from .bev_ops import _dev, _device_of, _ptr, _require_cuda, _stream_ptr, to_numpy_fresh, workspace
 from .constants import GRID_HEIGHT_PX, GRID_WIDTH_PX, INTENTIONS_MAP
 
 _CV_PI = 3.1415926535897932384626433832795
@@ -125,26 +125,28 @@ def augment_grid(src: torch.Tensor, params: Sequence[AugParams], out: Optional[t
                  two_pass: bool = True) -> torch.Tensor:
     """Apply per-frame ``params`` to ``src`` [B,C,400,720] (float32 CUDA); returns a new tensor (dst != src)."""
     _require_cuda()
-    if src.dim() != 4 or src.shape[2:] != (GRID_HEIGHT_PX, GRID_WIDTH_PX) or src.dtype != torch.float32:
-        raise ValueError("src must be float32 [B,C,400,720]")
+    if src.dim() != 4 or src.shape[2:] != (GRID_HEIGHT_PX, GRID_WIDTH_PX) or src.dtype != torch.float32 or not src.is_cuda:
+        raise ValueError("src must be a float32 CUDA tensor [B,C,400,720]")
     src = src.contiguous()
     B, Cc = int(src.shape[0]), int(src.shape[1])
     if len(params) != B:
         raise ValueError("one AugParams per frame")
     if out is None:
         out = torch.empty_like(src)
-    elif out.shape != src.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.data_ptr() == src.data_ptr():
-        raise ValueError("out must be a distinct contiguous float32 tensor of the same shape")
+    elif (out.shape != src.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != src.device
+          or out.data_ptr() == src.data_ptr()):
+        raise ValueError("out must be a distinct contiguous float32 tensor of the same shape on the same device")
     hparams = pack_params(params)
-    dparams = _dev(hparams, torch.uint8, src.device)
-    # scratch for the frames that rotate AND scale (two 4-tap passes instead of one 16-tap gather)
-    n_both = sum(1 for p in params if p.angle_deg is not None and p.scale is not None)
-    ws, wbytes = None, 0
-    if n_both and two_pass:
-        wbytes = n_both * Cc * GRID_HEIGHT_PX * GRID_WIDTH_PX * 4
-        ws = workspace.get(("augment", Cc), wbytes, src.device)
-    rc = _native.lib().bevgen_augment(_ptr(src), _ptr(out), B, Cc, _ptr(dparams), C.c_void_p(hparams.ctypes.data),
-                                      _ptr(ws), wbytes, _stream_ptr())
+    with torch.cuda.device(src.device):
+        dparams = _dev(hparams, torch.uint8, src.device)
+        # scratch for the frames that rotate AND scale (two 4-tap passes instead of one 16-tap gather)
+        n_both = sum(1 for p in params if p.angle_deg is not None and p.scale is not None)
+        ws, wbytes = None, 0
+        if n_both and two_pass:
+            wbytes = n_both * Cc * GRID_HEIGHT_PX * GRID_WIDTH_PX * 4
+            ws = workspace.get(("augment", Cc), wbytes, src.device)
+        rc = _native.lib().bevgen_augment(_ptr(src), _ptr(out), B, Cc, _ptr(dparams), C.c_void_p(hparams.ctypes.data),
+                                          _ptr(ws), wbytes, _stream_ptr())
     _native.check(rc, "bevgen_augment")
     return out
 
@@ -164,31 +166,33 @@ def lidar_bev_augmented(points4: torch.Tensor, sweep_offsets: torch.Tensor, rel_
     records (csrc/lidar_aug_tile.cuh) instead of generate -> read back -> resample -> write.  Device tensors in
     (points4 float32 or float16 [N,4], sweep_offsets int32 [B*S+1], rel_tf float64 [B*S,16]); returns float32
     [B, S*29, 400, 720].  Raises if a frame's parameters are unsupported (see ``fused_supported``)."""
-    device = _require_cuda()
+    _require_cuda()
     B, S = int(num_frames), int(num_sweeps)
     if len(params) != B:
         raise ValueError("one AugParams per frame")
     if points4.dim() != 2 or points4.shape[1] != 4 or points4.dtype not in (torch.float32, torch.float16) or not points4.is_cuda:
         raise ValueError("points4 must be a CUDA tensor [N,4] float32 or float16")
-    pts = points4.contiguous()
-    off = _dev(sweep_offsets, torch.int32, device)
-    tf = _dev(rel_tf, torch.float64, device).reshape(-1, 16)
-    if off.numel() != B * S + 1 or tf.shape[0] != B * S:
-        raise ValueError("sweep_offsets must have B*S+1 entries and rel_tf B*S matrices")
+    device = points4.device
     shape = (B, S * 29, GRID_HEIGHT_PX, GRID_WIDTH_PX)
-    if out is None:
-        out = torch.empty(shape, dtype=torch.float32, device=device)
-    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
-        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
-    hparams = pack_params(params) if packed is None else packed
-    dparams = _dev(hparams, torch.uint8, device)
-    L = _native.lib()
-    n = int(pts.shape[0])
-    wbytes = int(L.bevgen_lidar_aug_workspace_bytes(n, B, S, sum(1 for p in params if p.needs_gather)))
-    ws = workspace.get("lidar", wbytes, device)
-    rc = L.bevgen_lidar_bev_augmented(_ptr(pts), 1 if pts.dtype == torch.float16 else 0, _ptr(off), _ptr(tf), B, S, n,
-                                      int(max_sweep_points), _ptr(dparams), C.c_void_p(hparams.ctypes.data), _ptr(out),
-                                      _ptr(ws), wbytes, _stream_ptr())
+    with torch.cuda.device(device):
+        pts = points4.contiguous()
+        off = _dev(sweep_offsets, torch.int32, device)
+        tf = _dev(rel_tf, torch.float64, device).reshape(-1, 16)
+        if off.numel() != B * S + 1 or tf.shape[0] != B * S:
+            raise ValueError("sweep_offsets must have B*S+1 entries and rel_tf B*S matrices")
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+            raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape} on {device}")
+        hparams = pack_params(params) if packed is None else packed
+        dparams = _dev(hparams, torch.uint8, device)
+        L = _native.lib()
+        n = int(pts.shape[0])
+        wbytes = int(L.bevgen_lidar_aug_workspace_bytes(n, B, S, sum(1 for p in params if p.needs_gather)))
+        ws = workspace.get("lidar", wbytes, device)
+        rc = L.bevgen_lidar_bev_augmented(_ptr(pts), 1 if pts.dtype == torch.float16 else 0, _ptr(off), _ptr(tf), B, S, n,
+                                          int(max_sweep_points), _ptr(dparams), C.c_void_p(hparams.ctypes.data), _ptr(out),
+                                          _ptr(ws), wbytes, _stream_ptr())
     _native.check(rc, "bevgen_lidar_bev_augmented")
     return out
 
@@ -230,7 +234,7 @@ def apply_gt(p: AugParams, boxes: np.ndarray, intentions: np.ndarray):
 
 # ------------------------------------------------------------------------------- reference signatures (numpy)
 def _apply_np(lidar_bev: np.ndarray, map_bev: np.ndarray, p: AugParams):
-    dev = _require_cuda()
+    dev = _device_of(lidar_bev, map_bev)
     lo = to_numpy_fresh(augment_grid(_dev(lidar_bev, torch.float32, dev)[None], [p])[0])
     mo = to_numpy_fresh(augment_grid(_dev(map_bev, torch.float32, dev)[None], [p])[0])
     return lo, mo
@@ -294,7 +298,7 @@ def augment_bev(lidar_bev, map_bev, gt_dict):
     p = draw_aug_params(random)
     apply_gt(p, boxes, intents)
     on_device = isinstance(lidar_bev, torch.Tensor)
-    dev = _require_cuda()
+    dev = _device_of(lidar_bev, map_bev)
     ld = lidar_bev if on_device else _dev(lidar_bev, torch.float32, dev)
     md = map_bev if isinstance(map_bev, torch.Tensor) else _dev(map_bev, torch.float32, dev)
     lo = augment_grid(ld[None], [p])[0]

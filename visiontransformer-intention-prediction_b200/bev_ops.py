@@ -17,6 +17,7 @@ No CPU fallback: every function here ends in a call into ``libbevgen_b200.so``.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Optional, Sequence
 
 import numpy as np
@@ -40,8 +41,31 @@ def _require_cuda() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _device_of(*objs) -> torch.device:
+    """Device the call runs on: that of the first CUDA tensor among ``objs`` (a BevGenerator on cuda:1 keeps working
+    when cuda:0 is the current device), else the current device.  Callers launch under ``torch.cuda.device(dev)``."""
+    for o in objs:
+        if isinstance(o, torch.Tensor) and o.is_cuda:
+            return o.device
+    return _require_cuda()
+
+
 def _stream_ptr() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_offsets(host_off: np.ndarray, n_points: int, max_sweep_points: Optional[int]) -> int:
+    """CSR offsets that are available on the host are validated here (device-resident ones are clamped inside the
+    kernels instead): monotone, inside the point array; returns the largest sweep.  ``max_sweep_points`` only sizes the
+    launch grid -- a value below the largest sweep is corrected rather than silently dropping points."""
+    off = np.asarray(host_off, np.int64)
+    if off.size == 0:
+        return 0
+    d = np.diff(off)
+    if off[0] < 0 or (d < 0).any() or off[-1] > n_points:
+        raise ValueError(f"sweep_offsets must be non-decreasing and within [0, {n_points}]")
+    biggest = int(d.max()) if d.size else 0
+    return biggest if max_sweep_points is None else max(int(max_sweep_points), biggest)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -56,20 +80,30 @@ def _dev(a, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
 
 
 class _Workspace:
-    """Grow-only scratch buffer per (device, purpose); kernels never allocate."""
+    """Grow-only scratch buffer per (purpose, device, CUDA stream); kernels never allocate.
+
+    The stream is part of the key: launches on different streams (two generators, a generator's LiDAR and map streams,
+    host threads with their own current streams) may overlap on the GPU and must not share counters / bins / bit planes.
+    A buffer is allocated under, and only ever used on, the stream it is keyed by, so torch's caching allocator needs no
+    ``record_stream``.  Launches on ONE stream are ordered and can share."""
 
     def __init__(self) -> None:
         self._bufs = {}
+        self._lock = threading.Lock()
 
     def get(self, key, nbytes: int, device: torch.device) -> torch.Tensor:
-        buf = self._bufs.get((key, device))
-        if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-            self._bufs[(key, device)] = buf
-        return buf
+        k = (key, device, torch.cuda.current_stream(device).cuda_stream)
+        with self._lock:
+            buf = self._bufs.get(k)
+            if buf is None or buf.numel() < nbytes:
+                with torch.cuda.device(device):
+                    buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+                self._bufs[k] = buf
+            return buf
 
     def clear(self) -> None:
-        self._bufs.clear()
+        with self._lock:
+            self._bufs.clear()
 
 
 workspace = _Workspace()
@@ -156,40 +190,42 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
     rel_tf         float64 [B*S,4,4]  ego_SE3_world @ sweep_SE3 (pose.sweep_rel_transforms)
     returns        float32 CUDA tensor [B, S*29, 400, 720]
     """
-    device = _require_cuda()
+    device = _device_of(points4, sweep_offsets, rel_tf, out)
     B, S = int(num_frames), int(num_sweeps)
     host_off = None
-    if not isinstance(sweep_offsets, torch.Tensor):
-        host_off = np.ascontiguousarray(sweep_offsets, dtype=np.int32)
+    if not isinstance(sweep_offsets, torch.Tensor) or not sweep_offsets.is_cuda:
+        host_off = np.ascontiguousarray(sweep_offsets.numpy() if isinstance(sweep_offsets, torch.Tensor) else sweep_offsets,
+                                        dtype=np.int32)
     half = (isinstance(points4, torch.Tensor) and points4.dtype == torch.float16) or \
            (isinstance(points4, np.ndarray) and points4.dtype == np.float16)
-    pts = _dev(points4, torch.float16 if half else torch.float32, device)
-    off = _dev(sweep_offsets, torch.int32, device)
-    tf = _dev(rel_tf, torch.float64, device).reshape(-1, 16)
-    if pts.dim() != 2 or pts.shape[1] != 4:
-        raise ValueError("points4 must be [N,4] float32 or float16 (x,y,z,intensity)")
-    if off.numel() != B * S + 1 or tf.shape[0] != B * S:
-        raise ValueError("sweep_offsets must have B*S+1 entries and rel_tf B*S matrices")
-    n = int(pts.shape[0])
-    if max_sweep_points is None:
-        if host_off is None:
-            host_off = off.cpu().numpy()
-        max_sweep_points = int(np.diff(host_off).max()) if B * S else 0
-    f, r, c = _aug_fusion_args(B, flip, drop_rects, drop_counts, device)
-    shape = (B, S * LIDAR_HEIGHT_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
-    if out is None:
-        out = torch.empty(shape, dtype=torch.float32, device=device)
-    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
-        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
-    L = _native.lib()
-    ws = None
-    wbytes = 0
-    if algo == ALGO_TILED:
-        wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
-        ws = workspace.get("lidar", wbytes, device)
-    fn = L.bevgen_lidar_bev_fused_f16 if half else L.bevgen_lidar_bev_fused
-    rc = fn(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
-            _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
+    with torch.cuda.device(device):
+        pts = _dev(points4, torch.float16 if half else torch.float32, device)
+        off = _dev(sweep_offsets, torch.int32, device)
+        tf = _dev(rel_tf, torch.float64, device).reshape(-1, 16)
+        if pts.dim() != 2 or pts.shape[1] != 4:
+            raise ValueError("points4 must be [N,4] float32 or float16 (x,y,z,intensity)")
+        if off.numel() != B * S + 1 or tf.shape[0] != B * S:
+            raise ValueError("sweep_offsets must have B*S+1 entries and rel_tf B*S matrices")
+        n = int(pts.shape[0])
+        if host_off is not None:
+            max_sweep_points = _check_offsets(host_off, n, max_sweep_points)
+        elif max_sweep_points is None:
+            max_sweep_points = _check_offsets(off.cpu().numpy(), n, None)
+        f, r, c = _aug_fusion_args(B, flip, drop_rects, drop_counts, device)
+        shape = (B, S * LIDAR_HEIGHT_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+            raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape} on {device}")
+        L = _native.lib()
+        ws = None
+        wbytes = 0
+        if algo == ALGO_TILED:
+            wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
+            ws = workspace.get("lidar", wbytes, device)
+        fn = L.bevgen_lidar_bev_fused_f16 if half else L.bevgen_lidar_bev_fused
+        rc = fn(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
+                _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
     _native.check(rc, "bevgen_lidar_bev_fused")
     return out
 
@@ -198,32 +234,36 @@ def lidar_bev_from_ego_points(points3, intensity, sweep_offsets, num_frames: int
                               max_sweep_points: Optional[int] = None, flip=None, drop_rects=None, drop_counts=None,
                               out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
     """utils.py:62-106 on float64 points that are already in the ego frame (batched)."""
-    device = _require_cuda()
+    device = _device_of(points3, intensity, sweep_offsets, out)
     B, S = int(num_frames), int(num_sweeps)
-    host_off = None if isinstance(sweep_offsets, torch.Tensor) else np.ascontiguousarray(sweep_offsets, dtype=np.int32)
-    pts = _dev(points3, torch.float64, device)
-    inten = _dev(intensity, torch.float32, device)
-    off = _dev(sweep_offsets, torch.int32, device)
-    if pts.dim() != 2 or pts.shape[1] != 3 or inten.numel() != pts.shape[0] or off.numel() != B * S + 1:
-        raise ValueError("points3 [N,3] float64, intensity [N] float32, sweep_offsets [B*S+1] expected")
-    n = int(pts.shape[0])
-    if max_sweep_points is None:
-        if host_off is None:
-            host_off = off.cpu().numpy()
-        max_sweep_points = int(np.diff(host_off).max()) if B * S else 0
-    f, r, c = _aug_fusion_args(B, flip, drop_rects, drop_counts, device)
-    shape = (B, S * LIDAR_HEIGHT_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
-    if out is None:
-        out = torch.empty(shape, dtype=torch.float32, device=device)
-    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
-        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
-    L = _native.lib()
-    ws, wbytes = None, 0
-    if algo == ALGO_TILED:
-        wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
-        ws = workspace.get("lidar", wbytes, device)
-    rc = L.bevgen_lidar_bev_ego_f64(_ptr(pts), _ptr(inten), _ptr(off), B, S, n, int(max_sweep_points),
-                                    _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
+    host_off = None
+    if not isinstance(sweep_offsets, torch.Tensor) or not sweep_offsets.is_cuda:
+        host_off = np.ascontiguousarray(sweep_offsets.numpy() if isinstance(sweep_offsets, torch.Tensor) else sweep_offsets,
+                                        dtype=np.int32)
+    with torch.cuda.device(device):
+        pts = _dev(points3, torch.float64, device)
+        inten = _dev(intensity, torch.float32, device)
+        off = _dev(sweep_offsets, torch.int32, device)
+        if pts.dim() != 2 or pts.shape[1] != 3 or inten.numel() != pts.shape[0] or off.numel() != B * S + 1:
+            raise ValueError("points3 [N,3] float64, intensity [N] float32, sweep_offsets [B*S+1] expected")
+        n = int(pts.shape[0])
+        if host_off is not None:
+            max_sweep_points = _check_offsets(host_off, n, max_sweep_points)
+        elif max_sweep_points is None:
+            max_sweep_points = _check_offsets(off.cpu().numpy(), n, None)
+        f, r, c = _aug_fusion_args(B, flip, drop_rects, drop_counts, device)
+        shape = (B, S * LIDAR_HEIGHT_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+            raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape} on {device}")
+        L = _native.lib()
+        ws, wbytes = None, 0
+        if algo == ALGO_TILED:
+            wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
+            ws = workspace.get("lidar", wbytes, device)
+        rc = L.bevgen_lidar_bev_ego_f64(_ptr(pts), _ptr(inten), _ptr(off), B, S, n, int(max_sweep_points),
+                                        _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
     _native.check(rc, "bevgen_lidar_bev_ego_f64")
     return out
 

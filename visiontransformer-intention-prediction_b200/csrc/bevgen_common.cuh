@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/bevgen.h"
 
 namespace bevgen {
@@ -26,7 +28,15 @@ constexpr int kMaxRects = BEVGEN_MAX_DROP_RECTS;
 constexpr int kMapWordsPerRow = 24;                    // 768 bits >= 720 columns
 constexpr int kMapPlaneWords = kH * kMapWordsPerRow;   // 9 600 u32 per channel
 
-extern long long g_launch_count;           // host-side counter (cabi.cu)
+extern std::atomic<long long> g_launch_count;   // host-side counter (cabi.cu)
+
+// opt a kernel into `bytes` of dynamic shared memory on the CURRENT device (tracked per (kernel, device); cabi.cu)
+int ensure_dyn_smem(const void* kernel, int bytes);
+#define BEVGEN_DYN_SMEM(kernel, bytes)                                                   \
+    do {                                                                                 \
+        const int rc__ = ::bevgen::ensure_dyn_smem((const void*)(kernel), (int)(bytes)); \
+        if (rc__) return rc__;                                                           \
+    } while (0)
 
 #define BEVGEN_CHECK_LAUNCH()                                  \
     do {                                                       \

@@ -1,18 +1,22 @@
 // cabi.cu -- library-level entry points of the C ABI (include/bevgen.h).
 #include "bevgen_common.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace bevgen {
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 namespace {
 struct TimedLaunch { const char* name; cudaEvent_t e0, e1; };
-bool g_timing = false;
+std::atomic<bool> g_timing{false};
+std::mutex g_timing_mu;                    // guards the event lists below (launchers may be called from several host threads)
 std::vector<TimedLaunch> g_pending;
 std::vector<cudaEvent_t> g_event_pool;
 cudaEvent_t g_open = nullptr;
@@ -26,14 +30,36 @@ cudaEvent_t get_event() {
 }
 }  // namespace
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (kernel, device) pair, not to the process: a second GPU
+// driven from the same process needs its own call.  Remembered per pair under a mutex; raising it again is a no-op.
+int ensure_dyn_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lk(mu);
+    int& have = done[std::make_pair(kernel, dev)];
+    if (bytes <= have) return 0;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    have = bytes;
+    return 0;
+}
+
+// Timing is a single-caller developer / bench facility: begin/end pairs of one launch are bracketed by the same lock
+// holder only in the sense that the lists stay consistent; concurrent launchers may interleave their records.
 void timing_begin(const char* name, cudaStream_t st) {
     if (!g_timing) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
     g_open = get_event();
     g_open_name = name;
     cudaEventRecord(g_open, st);
 }
 void timing_end(cudaStream_t st) {
-    if (!g_timing || !g_open) return;
+    if (!g_timing) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    if (!g_open) return;
     cudaEvent_t e1 = get_event();
     cudaEventRecord(e1, st);
     g_pending.push_back({g_open_name, g_open, e1});
@@ -46,6 +72,7 @@ extern "C" void bevgen_timing_enable(int on) { bevgen::g_timing = on != 0; }
 // Synchronises the recorded events, writes "name count total_ms\n" lines into buf, clears the record.
 extern "C" int bevgen_timing_collect(char* buf, size_t cap) {
     using namespace bevgen;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
     std::map<std::string, std::pair<long long, double>> agg;
     for (auto& t : g_pending) {
         float ms = 0.f;
@@ -85,4 +112,4 @@ extern "C" const char* bevgen_error_string(int code) {
     return "bevgen: unknown error";
 }
 
-extern "C" int64_t bevgen_launch_count(void) { return bevgen::g_launch_count; }
+extern "C" int64_t bevgen_launch_count(void) { return bevgen::g_launch_count.load(); }

@@ -45,7 +45,18 @@ struct LidarIn {
     // alternative source of the per-frame fusions (bevgen_lidar_bev_augmented): flip always; dropout rectangles only for
     // frames that are not resampled afterwards (the fused tile kernel applies them to its output instead)
     const bevgen_aug_params* aug = nullptr;   // [B] or null
+    int n_points = 0x7FFFFFFF;                // rows in the point array: sweep ranges are clamped to [0, n_points)
 };
+
+// Row range of sweep `bs`, made safe against malformed CSR offsets (they live in device memory, the host cannot check them
+// without a synchronisation): clamped to the point array, empty when it is not ordered after the first offset.
+__device__ __forceinline__ void sweep_range(const LidarIn& in, int bs, int& beg, int& end) {
+    const int off0 = in.sweep_off[0];
+    beg = in.sweep_off[bs]; end = in.sweep_off[bs + 1];
+    beg = beg < 0 ? 0 : beg;
+    end = end > in.n_points ? in.n_points : end;
+    if (beg < off0 || off0 < 0) end = beg;
+}
 
 // Raw point as loaded from HBM.  Loads are issued for ALL of a thread's items before the first use, so
 // kBinItems independent 16 B (MODE 0) / 28 B (MODE 1) requests are in flight per thread.
@@ -178,13 +189,18 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
     uint32_t* const hist = reinterpret_cast<uint32_t*>(agg_smem + kAggChunk * 10);
     uint32_t* const base = hist + kTilesPerSweep;
     const int bs = bs0 + blockIdx.y, b = bs / in.S, tid = threadIdx.x;
-    const int beg = in.sweep_off[bs], end = in.sweep_off[bs + 1];
-    const long long chunk0 = (long long)beg + (long long)blockIdx.x * kAggChunk;
-    if (chunk0 >= end) return;
+    int beg, end;
+    sweep_range(in, bs, beg, end);
+    if ((long long)beg + (long long)blockIdx.x * kAggChunk >= end) return;
     __shared__ double sT[12];
     __shared__ int sRect[kMaxRects * 4];
+    __shared__ uint32_t s_spill_n, s_spill_base;
     int nrect; bool flip;
     load_frame_consts(in, bs, b, MODE, sT, sRect, nrect, flip);
+    // The grid's x extent comes from the caller's max_sweep_points (a sizing hint): a sweep longer than that is still
+    // binned completely, its CTAs walk the remaining chunks (normally this loop runs once).
+#pragma unroll 1
+    for (uint32_t chunk0 = (uint32_t)beg + blockIdx.x * (uint32_t)kAggChunk; chunk0 < (uint32_t)end; chunk0 += gridDim.x * (uint32_t)kAggChunk) {
     for (int i = tid; i < kTilesPerSweep; i += kAggThreads) hist[i] = 0;
     __syncthreads();
     // phase 1: records + per-tile rank inside the CTA (shared atomics)
@@ -193,16 +209,16 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
         RawPoint<MODE> raw[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const long long i = chunk0 + (long long)(g + u) * kAggThreads + tid;
-            raw[u] = load_point<MODE>(in, i, i < end);
+            const uint32_t i = chunk0 + (uint32_t)((g + u) * kAggThreads + tid);      // < 2^32: n_points < 2^31, chunk < 2^13
+            raw[u] = load_point<MODE>(in, (long long)i, i < (uint32_t)end);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = (g + u) * kAggThreads + tid;
-            const long long i = chunk0 + k;
+            const uint32_t i = chunk0 + (uint32_t)k;
             Voxel v;
             v.bits = 0;
-            const bool ok = (i < end) && point_voxel<MODE>(raw[u], sT, flip, sRect, nrect, v);
+            const bool ok = (i < (uint32_t)end) && point_voxel<MODE>(raw[u], sT, flip, sRect, nrect, v);
             uint32_t word = 0xFFFFFFFFu;
             if (ok) {
                 const uint32_t band = (uint32_t)v.py / kFillRows;
@@ -233,7 +249,6 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
     }
     __syncthreads();
     // phase 3: records to their slots; spills are ranked inside the CTA first (one shared atomic per warp) ...
-    __shared__ uint32_t s_spill_n, s_spill_base;
     if (tid == 0) s_spill_n = 0;
     __syncthreads();
     const int lane = tid & 31;
@@ -261,7 +276,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
     }
     __syncthreads();
     // ... phase 4: ONE global list-append atomic per CTA, then the spilled records go out
-    if (s_spill_n == 0) return;                                      // uniform
+    if (s_spill_n == 0) continue;                                    // uniform
     // per-sweep lists: sweep bs owns ovf[sweep_off[bs] - sweep_off[0] ...) (a point spills at most once), count in ovf_cnt[bs]
     if (tid == 0) s_spill_base = atomicAdd(ovf_cnt + bs, s_spill_n);
     __syncthreads();
@@ -276,6 +291,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
         o.bits = r.y; o.pad = 0;
         ovf[obase + rank[k]] = o;
     }
+    }   // chunk loop
 }
 
 __global__ void __launch_bounds__(128) k_tile_store(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
@@ -344,14 +360,17 @@ __global__ void __launch_bounds__(128) k_zero_fill_tma(unsigned char* __restrict
 template <int MODE>
 __global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint32_t* __restrict__ out, int bs0) {
     const int bs = bs0 + blockIdx.y, b = bs / in.S;
-    const int beg = in.sweep_off[bs], end = in.sweep_off[bs + 1];
-    const long long chunk0 = (long long)beg + (long long)blockIdx.x * kBinChunk;
-    if (chunk0 >= end) return;
+    int beg, end;
+    sweep_range(in, bs, beg, end);
+    if ((long long)beg + (long long)blockIdx.x * kBinChunk >= end) return;
     __shared__ double sT[12];
     __shared__ int sRect[kMaxRects * 4];
     int nrect; bool flip;
     load_frame_consts(in, bs, b, MODE, sT, sRect, nrect, flip);
     __syncthreads();
+    // grid x extent = the caller's max_sweep_points hint; longer sweeps are still covered (loop normally runs once)
+#pragma unroll 1
+    for (long long chunk0 = (long long)beg + (long long)blockIdx.x * kBinChunk; chunk0 < end; chunk0 += (long long)gridDim.x * kBinChunk) {
     RawPoint<MODE> raw[kBinItems];
 #pragma unroll
     for (int it = 0; it < kBinItems; ++it) {
@@ -373,6 +392,7 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint
 #pragma unroll
     for (int it = 0; it < kBinItems; ++it)
         if (addr[it]) atomicMax(addr[it], val[it]);
+    }   // chunk loop
 }
 
 template <typename T>
@@ -408,9 +428,11 @@ TiledWorkspace tiled_layout(long long total_points, int B, int S, int n_resample
 }
 
 template <int MODE>
-int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int max_sweep_points, float* out,
+int launch_lidar(LidarIn in, int B, int S, long long total_points, int max_sweep_points, float* out,
                  void* workspace, size_t workspace_bytes, int algo, cudaStream_t st) {
-    if (B <= 0 || S <= 0 || total_points < 0 || max_sweep_points < 0 || !out || !in.sweep_off) return BEVGEN_E_INVALID_ARG;
+    if (B <= 0 || S <= 0 || total_points < 0 || total_points > 0x7FFFFFFFll || max_sweep_points < 0 || !out || !in.sweep_off)
+        return BEVGEN_E_INVALID_ARG;
+    in.n_points = (int)total_points;
     if ((in.rects == nullptr) != (in.nrects == nullptr)) return BEVGEN_E_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;      // TMA bulk stores need 16 B alignment
     const size_t ntiles = (size_t)B * S * kTilesPerSweep;
@@ -445,11 +467,7 @@ int launch_lidar(const LidarIn& in, int B, int S, long long total_points, int ma
         uint2* bins = reinterpret_cast<uint2*>(wp + L.bins);
         OvfRec* ovf = reinterpret_cast<OvfRec*>(wp + L.ovf);
         BEVGEN_CUDA(cudaMemsetAsync(cnt, 0, (ntiles + (size_t)B * S + 64) * 4, st));
-        static bool attr_set[3] = {false, false, false};
-        if (!attr_set[MODE]) {
-            BEVGEN_CUDA(cudaFuncSetAttribute(k_bin_fixed<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAggSmem));
-            attr_set[MODE] = true;
-        }
+        BEVGEN_DYN_SMEM(k_bin_fixed<MODE>, kAggSmem);
         // (Measured: splitting the batch into frame groups, with or without overlapping the binning of group g+1 with
         //  the stores of group g on a second stream, is slower than these three whole-batch launches.)
         if (chunks > 0) {
@@ -473,8 +491,10 @@ template <int MODE>
 int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int max_sweep_points,
                            const bevgen_aug_params* params_host, float* out, void* workspace, size_t workspace_bytes,
                            cudaStream_t st) {
-    if (B <= 0 || S <= 0 || total_points < 0 || max_sweep_points < 0 || !out || !in.sweep_off || !in.aug || !params_host)
+    if (B <= 0 || S <= 0 || total_points < 0 || total_points > 0x7FFFFFFFll || max_sweep_points < 0 || !out || !in.sweep_off ||
+        !in.aug || !params_host)
         return BEVGEN_E_INVALID_ARG;
+    in.n_points = (int)total_points;
     if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
     const size_t ntiles = (size_t)B * S * kTilesPerSweep;
     if (ntiles > 0x7FFFFFFFull || (unsigned)(B * S) > 65535u || B > 32767) return BEVGEN_E_UNSUPPORTED;
@@ -493,18 +513,10 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
     uint32_t* cnt2 = reinterpret_cast<uint32_t*>(wp + L.cnt2);
     uint2* bins2 = reinterpret_cast<uint2*>(wp + L.bins2);
     BEVGEN_CUDA(cudaMemsetAsync(cnt, 0, (ntiles + (size_t)B * S + 64) * 4, st));
-    static bool attr_set[3] = {false, false, false};
-    if (!attr_set[MODE]) {
-        BEVGEN_CUDA(cudaFuncSetAttribute(k_bin_fixed<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAggSmem));
-        attr_set[MODE] = true;
-    }
-    static bool aug_attr_set = false;
-    if (!aug_attr_set) {
-        BEVGEN_CUDA(cudaFuncSetAttribute(k_tile_aug<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AugTileCfg<true, false>::kSmem));
-        BEVGEN_CUDA(cudaFuncSetAttribute(k_tile_aug<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AugTileCfg<false, true>::kSmem));
-        BEVGEN_CUDA(cudaFuncSetAttribute(k_tile_aug<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AugTileCfg<true, true>::kSmem));
-        aug_attr_set = true;
-    }
+    BEVGEN_DYN_SMEM(k_bin_fixed<MODE>, kAggSmem);
+    BEVGEN_DYN_SMEM((k_tile_aug<true, false>), (AugTileCfg<true, false>::kSmem));
+    BEVGEN_DYN_SMEM((k_tile_aug<false, true>), (AugTileCfg<false, true>::kSmem));
+    BEVGEN_DYN_SMEM((k_tile_aug<true, true>), (AugTileCfg<true, true>::kSmem));
     const bool have_points = max_sweep_points > 0;
     if (have_points) {
         const dim3 agg_grid((max_sweep_points + kAggChunk - 1) / kAggChunk, B * S);

@@ -343,11 +343,7 @@ int draw_maps(const double* verts, const int32_t* pl_off, const int32_t* lanes, 
         if (max_polyline_verts < 1 || max_polyline_verts > BEVGEN_MAX_POLYLINE_VERTS) return BEVGEN_E_UNSUPPORTED;
         const int maxv = (max_polyline_verts + 31) / 32 * 32;
         const size_t smem = (size_t)kDrawWarps * ((size_t)maxv * 2 * sizeof(short2) + (size_t)maxv * 4 * sizeof(int));
-        static size_t attr_smem = 0;
-        if (smem > 48 * 1024 && smem > attr_smem) {
-            BEVGEN_CUDA(cudaFuncSetAttribute(k_map_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_smem = smem;
-        }
+        if (smem > 48 * 1024) BEVGEN_DYN_SMEM(k_map_draw, smem);
         const dim3 grid((max_prims + kDrawWarps - 1) / kDrawWarps, B);
         BEVGEN_LAUNCH("k_map_draw", st, k_map_draw<<<grid, kDrawThreads, smem, st>>>(in, planes, maxv));
     }

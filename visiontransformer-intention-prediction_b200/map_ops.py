@@ -23,7 +23,9 @@ class MapTable:
     """Concatenation of FlatMaps on one device; ``frame_rows[m]`` = (lane_begin, lane_count, cw_begin, cw_count)."""
 
     def __init__(self, flat_maps: Sequence[maps.FlatMap], device: Optional[torch.device] = None) -> None:
-        device = device or _require_cuda()
+        device = torch.device(device) if device is not None else _require_cuda()
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         verts, pl_off, lanes, cws, rows = [], [np.zeros(1, np.int64)], [], [], []
         v_base = p_base = l_base = c_base = 0
         max_len = 0
@@ -55,30 +57,40 @@ class MapTable:
         return self.frame_rows.shape[0]
 
 
+def _frame_rows(table: MapTable, map_ids) -> np.ndarray:
+    """(lane_begin, lane_count, cw_begin, cw_count) per frame.  -1 is FrameBatch's "no map" marker and must not reach
+    numpy indexing (it would wrap to the last map): ids outside [0, num_maps) are an error."""
+    ids = np.asarray(map_ids, np.int64).reshape(-1)
+    if ids.size and (ids.min() < 0 or ids.max() >= table.num_maps):
+        raise ValueError(f"map ids must be in [0, {table.num_maps}); got min {int(ids.min())}, max {int(ids.max())} "
+                         "(-1 means 'no map': such frames cannot be rasterised)")
+    return table.frame_rows[ids]
+
+
 def rasterize_maps(table: MapTable, map_ids, ego_T, *, flip=None, drop_rects=None, drop_counts=None,
                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """utils.py:108-182 for a batch: frame b uses map ``map_ids[b]`` of ``table`` and the 3x3 matrix
     ``ego_T[b]`` (pose.map_matrix_from_pose).  Returns float32 CUDA ``[B,9,400,720]``."""
     device = table.device
-    ids = np.asarray(map_ids, np.int64).reshape(-1)
-    B = ids.shape[0]
-    rows = table.frame_rows[ids]
-    T = _dev(np.asarray(ego_T, np.float64).reshape(B, 9) if not isinstance(ego_T, torch.Tensor) else ego_T,
-             torch.float64, device).reshape(B, 9)
-    fmap = _dev(rows, torch.int32, device)
-    max_prims = int((rows[:, 1] + rows[:, 3]).max()) if B else 0
-    f, r, c = _aug_fusion_args(B, flip, drop_rects, drop_counts, device)
+    rows = _frame_rows(table, map_ids)
+    B = rows.shape[0]
     shape = (B, MAP_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
-    if out is None:
-        out = torch.empty(shape, dtype=torch.float32, device=device)
-    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
-        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
-    L = _native.lib()
-    wbytes = int(L.bevgen_map_workspace_bytes(B))
-    ws = workspace.get("map", wbytes, device)
-    rc = L.bevgen_map_raster(_ptr(table.verts), _ptr(table.pl_off), _ptr(table.lanes), _ptr(table.cws), _ptr(fmap),
-                             _ptr(T), B, max_prims, int(table.max_polyline_len), _ptr(f), _ptr(r), _ptr(c), _ptr(out),
-                             _ptr(ws), wbytes, _stream_ptr())
+    with torch.cuda.device(device):
+        T = _dev(np.asarray(ego_T, np.float64).reshape(B, 9) if not isinstance(ego_T, torch.Tensor) else ego_T,
+                 torch.float64, device).reshape(B, 9)
+        fmap = _dev(rows, torch.int32, device)
+        max_prims = int((rows[:, 1] + rows[:, 3]).max()) if B else 0
+        f, r, c = _aug_fusion_args(B, flip, drop_rects, drop_counts, device)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+            raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape} on {device}")
+        L = _native.lib()
+        wbytes = int(L.bevgen_map_workspace_bytes(B))
+        ws = workspace.get("map", wbytes, device)
+        rc = L.bevgen_map_raster(_ptr(table.verts), _ptr(table.pl_off), _ptr(table.lanes), _ptr(table.cws), _ptr(fmap),
+                                 _ptr(T), B, max_prims, int(table.max_polyline_len), _ptr(f), _ptr(r), _ptr(c), _ptr(out),
+                                 _ptr(ws), wbytes, _stream_ptr())
     _native.check(rc, "bevgen_map_raster")
     return out
 
@@ -91,28 +103,28 @@ def rasterize_maps_augmented(table: MapTable, map_ids, ego_T, params, *, out: Op
     import ctypes as C
     from . import augment as _aug
     device = table.device
-    ids = np.asarray(map_ids, np.int64).reshape(-1)
-    B = ids.shape[0]
+    rows = _frame_rows(table, map_ids)
+    B = rows.shape[0]
     if len(params) != B:
         raise ValueError("one AugParams per frame")
-    rows = table.frame_rows[ids]
-    T = _dev(np.asarray(ego_T, np.float64).reshape(B, 9) if not isinstance(ego_T, torch.Tensor) else ego_T,
-             torch.float64, device).reshape(B, 9)
-    fmap = _dev(rows, torch.int32, device)
-    max_prims = int((rows[:, 1] + rows[:, 3]).max()) if B else 0
     shape = (B, MAP_CHANNELS, GRID_HEIGHT_PX, GRID_WIDTH_PX)
-    if out is None:
-        out = torch.empty(shape, dtype=torch.float32, device=device)
-    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
-        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
-    hparams = _aug.pack_params(params) if packed is None else packed
-    dparams = _dev(hparams, torch.uint8, device)
-    L = _native.lib()
-    wbytes = int(L.bevgen_map_workspace_bytes(B))
-    ws = workspace.get("map", wbytes, device)
-    rc = L.bevgen_map_raster_augmented(_ptr(table.verts), _ptr(table.pl_off), _ptr(table.lanes), _ptr(table.cws), _ptr(fmap),
-                                       _ptr(T), B, max_prims, int(table.max_polyline_len), _ptr(dparams),
-                                       C.c_void_p(hparams.ctypes.data), _ptr(out), _ptr(ws), wbytes, _stream_ptr())
+    with torch.cuda.device(device):
+        T = _dev(np.asarray(ego_T, np.float64).reshape(B, 9) if not isinstance(ego_T, torch.Tensor) else ego_T,
+                 torch.float64, device).reshape(B, 9)
+        fmap = _dev(rows, torch.int32, device)
+        max_prims = int((rows[:, 1] + rows[:, 3]).max()) if B else 0
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+            raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape} on {device}")
+        hparams = _aug.pack_params(params) if packed is None else packed
+        dparams = _dev(hparams, torch.uint8, device)
+        L = _native.lib()
+        wbytes = int(L.bevgen_map_workspace_bytes(B))
+        ws = workspace.get("map", wbytes, device)
+        rc = L.bevgen_map_raster_augmented(_ptr(table.verts), _ptr(table.pl_off), _ptr(table.lanes), _ptr(table.cws),
+                                           _ptr(fmap), _ptr(T), B, max_prims, int(table.max_polyline_len), _ptr(dparams),
+                                           C.c_void_p(hparams.ctypes.data), _ptr(out), _ptr(ws), wbytes, _stream_ptr())
     _native.check(rc, "bevgen_map_raster_augmented")
     return out
 

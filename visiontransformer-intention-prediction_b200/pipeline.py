@@ -99,7 +99,11 @@ class BevGenerator:
 
     def __init__(self, map_table: Optional[map_ops.MapTable] = None, algo: int = bev_ops.ALGO_TILED,
                  device: Optional[torch.device] = None, fused_augment: bool = True, map_stream_priority: int = 0) -> None:
-        self.device = device or bev_ops._require_cuda()
+        self.device = torch.device(device) if device is not None else bev_ops._require_cuda()
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if map_table is not None and map_table.device != self.device:
+            raise ValueError(f"map table lives on {map_table.device}, generator on {self.device}")
         self.map_table = map_table
         self.algo = algo
         # LiDAR frames that rotate / scale: built directly in augmented form from the binned point records (one write of
@@ -132,6 +136,10 @@ class BevGenerator:
         rotate or scale are built directly in augmented form (LiDAR from the binned point records, map channels from
         the rasterizer's bit planes) -- or, with ``fused_augment=False`` / parameters outside the fused kernel's reach,
         generated into scratch and resampled by the dense gather kernel.  Same bits either way."""
+        with torch.cuda.device(self.device):      # the generator's device, whatever the caller's current device is
+            return self._generate(batch, aug, dev, with_map, out_lidar, out_map)
+
+    def _generate(self, batch, aug, dev, with_map, out_lidar, out_map) -> dict:
         B, S = batch.num_frames, batch.num_sweeps
         dv = dev if dev is not None else self.upload(batch)
         flip = rects = cnt = None

@@ -9,12 +9,14 @@ points packed as ``[N,4]`` rows (x, y, z, intensity) in the narrowest exact dtyp
 * float16 when every column is exactly representable (AV2 stores x,y,z as float16 and intensity as uint8) -> 8 B/point;
 * float32 otherwise.
 
-Decoded sweeps are cached per path (one parse per file instead of one per sample that uses the sweep: with 10-sweep
-sliding windows every file is otherwise read ten times per epoch).
+Decoded sweeps go through a byte-bounded LRU (default 256 MiB, ``set_cache_bytes``): with 10-sweep sliding windows
+every file is otherwise parsed ten times per epoch, and a small window of recent sweeps captures that reuse.
 """
 from __future__ import annotations
 
+import collections
 import dataclasses
+import threading
 from pathlib import Path
 from typing import Dict, Optional, Sequence
 
@@ -23,7 +25,74 @@ import numpy as np
 from . import pose as _pose
 
 _COLUMNS = ["x", "y", "z", "intensity"]
-_CACHE: Dict[str, Optional[np.ndarray]] = {}
+
+
+class _SweepCache:
+    """Byte-bounded LRU of decoded sweeps.  With 10-sweep sliding windows consecutive samples of a log share 9 of their
+    10 files, so a small window of recent sweeps captures nearly all the reuse; an unbounded cache would grow to the whole
+    split (~100 k files x ~0.8 MB) over an epoch.  The reference keeps no per-sweep state at all (dataset.py:305-321)."""
+
+    DEFAULT_BYTES = 256 << 20          # ~300 sweeps of 100 k points at 8 B/point
+
+    def __init__(self, max_bytes: int = DEFAULT_BYTES) -> None:
+        self.max_bytes = int(max_bytes)
+        self._d: "collections.OrderedDict[str, Optional[np.ndarray]]" = collections.OrderedDict()
+        self._bytes = 0
+        self._lock = threading.Lock()
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _size(v: Optional[np.ndarray]) -> int:
+        return 64 if v is None else int(v.nbytes) + 64
+
+    def get(self, key: str):
+        with self._lock:
+            if key in self._d:
+                self._d.move_to_end(key)
+                self.hits += 1
+                return True, self._d[key]
+            self.misses += 1
+            return False, None
+
+    def put(self, key: str, value: Optional[np.ndarray]) -> None:
+        sz = self._size(value)
+        with self._lock:
+            if key in self._d:
+                self._bytes -= self._size(self._d.pop(key))
+            if sz > self.max_bytes:
+                return                  # larger than the whole budget: not cached
+            self._d[key] = value
+            self._bytes += sz
+            while self._bytes > self.max_bytes and self._d:
+                _, old = self._d.popitem(last=False)
+                self._bytes -= self._size(old)
+
+    def resize(self, max_bytes: int) -> None:
+        with self._lock:
+            self.max_bytes = int(max_bytes)
+            while self._bytes > self.max_bytes and self._d:
+                _, old = self._d.popitem(last=False)
+                self._bytes -= self._size(old)
+
+    def clear(self) -> None:
+        with self._lock:
+            self._d.clear()
+            self._bytes = 0
+
+    @property
+    def nbytes(self) -> int:
+        return self._bytes
+
+    def __len__(self) -> int:
+        return len(self._d)
+
+
+_CACHE = _SweepCache()
+
+
+def set_cache_bytes(max_bytes: int) -> None:
+    """Resize the decoded-sweep LRU (0 disables caching)."""
+    _CACHE.resize(max_bytes)
 
 
 def decode_sweep(path, use_cache: bool = True) -> Optional[np.ndarray]:
@@ -32,8 +101,10 @@ def decode_sweep(path, use_cache: bool = True) -> Optional[np.ndarray]:
     import pyarrow as pa
     import pyarrow.feather as feather
     key = str(path)
-    if use_cache and key in _CACHE:
-        return _CACHE[key]
+    if use_cache:
+        hit, val = _CACHE.get(key)
+        if hit:
+            return val
     out: Optional[np.ndarray] = None
     p = Path(key)
     if p.is_file():
@@ -52,7 +123,7 @@ def decode_sweep(path, use_cache: bool = True) -> Optional[np.ndarray]:
             print(f"Warning: Corrupt LiDAR sweep file: {key}. Skipping sweep.")
             out = None
     if use_cache:
-        _CACHE[key] = out
+        _CACHE.put(key, out)
     return out
 
 
@@ -78,9 +149,12 @@ def _pose_row(ego_poses_df, ts) -> Optional[np.ndarray]:
     return np.array([r["tx_m"], r["ty_m"], r["tz_m"], r["qx"], r["qy"], r["qz"], r["qw"]], dtype=np.float64)
 
 
-def load_frame(log_dir, sweep_ts_list: Sequence[int], current_ts_ns: int, ego_poses_df) -> Optional[SweepFrame]:
+def load_frame(log_dir, sweep_ts_list: Sequence[int], current_ts_ns: int, ego_poses_df, *,
+               use_cache: bool = True) -> Optional[SweepFrame]:
     """dataset.py:285-342 without the CPU transform: returns ``None`` where the reference returns ``None``
-    (no current pose row :286-287, invalid current quaternion :294-296, every sweep missing :344-345)."""
+    (no current pose row :286-287, invalid current quaternion :294-296, every sweep missing :344-345).
+    ``use_cache=False`` decodes every file afresh (the reference's behaviour); the default goes through the
+    byte-bounded LRU (``set_cache_bytes``)."""
     cur = _pose_row(ego_poses_df, current_ts_ns)
     if cur is None:
         return None
@@ -96,7 +170,7 @@ def load_frame(log_dir, sweep_ts_list: Sequence[int], current_ts_ns: int, ego_po
     poses[:, 6] = 1.0                                            # identity for missing sweeps (never used: empty range)
     any_sweep = False
     for s, ts in enumerate(sweep_ts_list):
-        sweep = decode_sweep(base / f"{ts}.feather")
+        sweep = decode_sweep(base / f"{ts}.feather", use_cache=use_cache)
         if sweep is None:
             continue
         prow = _pose_row(ego_poses_df, ts)                       # dataset.py:323-326
