@@ -62,6 +62,28 @@ def make_frames(workload: str, batch: int, points: int, rank: int):
     return frames, md
 
 
+POINT_FORMATS = {
+    "av2": (7, "AV2 sweep columns as stored on disk and read by dataset.py:311-321: float16 x,y,z + uint8 intensity, 7 B/point"),
+    "f16": (8, "rows of 4 x float16 (x,y,z,intensity), 8 B/point"),
+    "f32": (16, "rows of 4 x float32 (x,y,z,intensity), 16 B/point"),
+}
+
+
+def workload_config(args) -> dict:
+    """The workload, identically on both arms (`--impl ours` / `--impl reference`): what one step processes per GPU."""
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
+    pb = POINT_FORMATS[args.points_dtype][0]
+    inputs_mb = B * 10 * args.points * pb / 1e6
+    return {"workload": wl["desc"], "batch_per_gpu": B, "sweeps": 10, "points_per_sweep": args.points,
+            "points_per_frame": 10 * args.points, "points_format": POINT_FORMATS[args.points_dtype][1],
+            "point_values": "synthetic float32 draws" + ("" if args.points_dtype == "f32" else
+                                                         " rounded to float16-representable coordinates (same values on both arms)"),
+            "arithmetic": "float64 pose transform and binning, float32 intensities (the reference's own precision and op order)",
+            "l2": f"no flush needed: per step inputs {inputs_mb:.0f} MB + outputs {B * LIDAR_FRAME_BYTES / 1e9:.1f} GB >> 126 MB L2",
+            "sharding": "frames independent per rank, no data-path collective"}
+
+
 def frame_bytes(frame_points: int, with_map: bool, map_verts: int, point_bytes: int = 16) -> int:
     """algorithmic bytes per frame."""
     b = frame_points * point_bytes + 10 * 128 + LIDAR_FRAME_BYTES
@@ -73,12 +95,14 @@ def frame_bytes(frame_points: int, with_map: bool, map_verts: int, point_bytes: 
 # ----------------------------------------------------------------------------------- CPU reference arm
 def _cpu_worker(args):
     """One frame through the numpy/OpenCV port, exactly the stages Dataset.__getitem__ runs."""
-    workload, points, idx, map_path, seed = args
+    workload, points, idx, map_path, seed, quantize = args
     import random as _r
     import bevgen_b200 as bg
     from oracle import numpy_port as npp
     syn = bg.synthetic
     f = syn.frame_c4(idx, n=points) if workload == "c4" else (syn.frame_c2(idx, n=points) if workload == "c2" else syn.frame_c3(idx, n=points, map_data={}))
+    if quantize:
+        f = syn.quantize_f16(f)          # the same point values our arm consumes
     t0 = time.perf_counter()
     lid = npp.frame_lidar(f.points4, f.sweep_offsets, f.sweep_poses, f.current_pose)
     if map_path:
@@ -91,7 +115,8 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_reference(workload: str, points: int, steps: int, warmup: int, workers: int, budget_s: float = 150.0):
+def cpu_reference(workload: str, points: int, steps: int, warmup: int, workers: int, budget_s: float = 150.0,
+                  quantize: bool = False):
     """frames/s of the CPU path with `workers` processes, each step = one frame per worker."""
     import multiprocessing as mp
     import tempfile
@@ -105,7 +130,7 @@ def cpu_reference(workload: str, points: int, steps: int, warmup: int, workers: 
     t_begin = time.perf_counter()
     with ctx.Pool(workers) as pool:
         for s in range(warmup + steps):
-            jobs = [(workload, points, s * workers + w, map_path, 1000 * 5 + s * workers + w) for w in range(workers)]
+            jobs = [(workload, points, s * workers + w, map_path, 1000 * 5 + s * workers + w, quantize) for w in range(workers)]
             t0 = time.perf_counter()
             pool.map(_cpu_worker, jobs, chunksize=1)
             dt = time.perf_counter() - t0
@@ -132,17 +157,19 @@ def run_reference(args) -> None:
         return
     workers = min(host_threads(), 32)
     wl = WORKLOADS[args.workload]
-    fps, step_s, nsteps = cpu_reference(args.workload, args.points, args.steps, args.warmup, workers)
+    fps, step_s, nsteps = cpu_reference(args.workload, args.points, args.steps, args.warmup, workers,
+                                        quantize=args.points_dtype != "f32")
     pts_frame = 10 * args.points
     line = {
         "impl": "reference", "metric": "bev_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": nsteps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "gpoints_per_s": fps * pts_frame / 1e9,
-        "config": {"workload": wl["desc"], "batch": workers, "sweeps": 10, "points_per_sweep": args.points,
-                   "note": "reference CPU path (numpy/OpenCV port of utils.py), one frame per worker process per step"},
+        "config": workload_config(args),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
-                         "sample": f"{nsteps} steps x {workers} frames ({workers} worker processes, library-default threads each)"},
+                         "sample": f"{nsteps} steps x {workers} frames of the configured workload: the reference's numpy/OpenCV call "
+                                   f"sequence (oracle/numpy_port.py), one frame per worker process per step, {workers} worker "
+                                   "processes with library-default threads each (the reference itself is single-process)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -214,7 +241,7 @@ def run_ours(args) -> None:
     B = args.batch or wl["batch"]
     algo = {"atomic": bg.ALGO_ATOMIC, "tiled": bg.ALGO_TILED, "memset": bg.ALGO_MEMSET_ATOMIC}[args.algo]
     frames, md = make_frames(args.workload, B, args.points, rank)
-    if args.points_dtype == "f16":
+    if args.points_dtype != "f32":
         frames = [bg.synthetic.quantize_f16(f) for f in frames]
     table = bg.MapTable([bg.maps.parse_map_dict(md)]) if wl["map"] else None
     aug = None
@@ -226,7 +253,7 @@ def run_ours(args) -> None:
             aug.append(bg.draw_aug_params(random))
         frames, aug, _ = bg.partition_for_augmentation(frames, aug)     # resampled frames first: no identity copies
     batch = bg.FrameBatch.pack(frames, 10, map_ids=[0] * B if wl["map"] else None,
-                               points_dtype=np.float16 if args.points_dtype == "f16" else np.float32)
+                               points_dtype={"f16": np.float16, "f32": np.float32, "av2": "av2"}[args.points_dtype])
     gen = bg.BevGenerator(table, algo=algo, device=dev, fused_augment=not args.dense_augment)
     S = 10
     out_l = torch.empty((B, S * 29, 400, 720), dtype=torch.float32, device=dev)
@@ -362,12 +389,13 @@ def run_ours(args) -> None:
     value = frames_total / (total_ms_plain / 1e3)
     pts_frame = int(batch.num_points / B)
     verts = int(table.verts.shape[0]) if table is not None else 0
-    fbytes = frame_bytes(pts_frame, wl["map"], verts, 8 if args.points_dtype == "f16" else 16)
+    pbytes = POINT_FORMATS[args.points_dtype][0]
+    fbytes = frame_bytes(pts_frame, wl["map"], verts, pbytes)
 
     kernels = {n: {"ms_per_step": ms / K, "launches_per_step": c / K} for n, (c, ms) in ktimes.items()}
     own_bytes = {   # algorithmic bytes one launch of each kernel must move, per frame
-        "k_zero_fill_tma": LIDAR_FRAME_BYTES, "cudaMemsetAsync": LIDAR_FRAME_BYTES, "k_scatter_atomic": pts_frame * 16,
-        "k_bin_fixed": pts_frame * 16, "k_tile_store": LIDAR_FRAME_BYTES, "k_overflow_red": 0,
+        "k_zero_fill_tma": LIDAR_FRAME_BYTES, "cudaMemsetAsync": LIDAR_FRAME_BYTES, "k_scatter_atomic": pts_frame * pbytes,
+        "k_bin_fixed": pts_frame * pbytes, "k_tile_store": LIDAR_FRAME_BYTES, "k_overflow_red": 0,
         "k_map_expand": MAP_FRAME_BYTES, "k_augment": 2 * (LIDAR_FRAME_BYTES + (MAP_FRAME_BYTES if wl["map"] else 0)),
         "k_tile_aug": LIDAR_FRAME_BYTES, "k_rebin_aug": 0,
     }
@@ -415,7 +443,8 @@ def run_ours(args) -> None:
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         workers = min(host_threads(), 32)
-        cfps, cstep, cn = cpu_reference(args.workload, args.points, 2, 1, workers, budget_s=60.0)
+        cfps, cstep, cn = cpu_reference(args.workload, args.points, 2, 1, workers, budget_s=60.0,
+                                        quantize=args.points_dtype != "f32")
         cpu = {"value": cfps, "unit": "frames/s", "cores": workers, "kind": "port",
                "sample": f"{cn} steps x {workers} frames of the same workload through oracle/numpy_port.py "
                          f"({workers} worker processes, one frame each per step; {cstep:.2f} s/step)"}
@@ -424,9 +453,8 @@ def run_ours(args) -> None:
         "metric": "bev_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": total_ms_plain / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "batch_per_gpu": B, "sweeps": S, "points_per_frame": pts_frame, "algo": args.algo, "points_dtype": args.points_dtype,
-                   "l2": f"per step inputs {batch.h2d_bytes/1e6:.0f} MB + outputs {B*LIDAR_FRAME_BYTES/1e9:.1f} GB >> 126 MB L2",
-                   "parity": parity, "sharding": "frames independent per rank, no data-path collective", "host_affinity": numa},
+        "config": workload_config(args),
+        "impl_notes": {"algo": args.algo, "points_dtype": args.points_dtype, "parity": parity, "host_affinity": numa},
         "gpoints_per_s": value * pts_frame / 1e9,
         "bytes_per_frame": fbytes, "step_algorithmic_gbs": step_gbs, "step_frac_of_peak": step_gbs / peak,
         "roofline": roofline, "kernels": kernels, "ms_per_step_with_event_timing": total_ms / K,
@@ -454,8 +482,11 @@ def main() -> None:
     ap.add_argument("--algo", default="tiled", choices=["atomic", "tiled", "memset"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--points", type=int, default=100_000, help="points per sweep")
-    ap.add_argument("--points-dtype", default="f32", choices=["f32", "f16"],
-                    help="f16: coordinates rounded to fp16-representable values (AV2 storage precision) and packed at 8 B/point")
+    ap.add_argument("--points-dtype", default="av2", choices=["av2", "f16", "f32"],
+                    help="host/device format of the input points.  av2 (default): AV2's on-disk sweep columns, float16 x,y,z + uint8 "
+                         "intensity, 7 B/point -- the dtypes the reference's Dataset reads (dataset.py:311-321); f16: 4 x float16 rows, "
+                         "8 B/point; f32: float32 rows, 16 B/point with unrounded coordinates.  av2 / f16 round the synthetic coordinates "
+                         "to float16-representable values on BOTH arms; all arithmetic stays float64 / float32 as in the reference")
     ap.add_argument("--dense-augment", action="store_true",
                     help="config 5: take the dense route (generate -> gather) instead of the fused generation+augmentation kernel")
     ap.add_argument("--e2e-repeats", type=int, default=3,

@@ -88,7 +88,10 @@ int bevgen_transform_points_f64(const double *pts, int64_t n, int64_t stride, co
  *   drop_rects  int32 [B, 5, 4] = (y0, x0, ph, pw); drop_counts int32 [B] (utils.py:496)
  *               -- only meaningful when no rotate/scale follows for that frame
  *
- * max_sweep_points: max over sweeps of the row count (host knows it; sizes the grid).
+ * max_sweep_points: max over sweeps of the row count -- a SIZING HINT for the launch grid (the host usually knows it): a
+ *                   sweep longer than the hint is still processed completely, only slower.
+ * sweep_offsets live in device memory and cannot be validated by the host without a synchronisation: the kernels clamp
+ * every range to [0, total_points) and treat a range that is not ordered after sweep_offsets[0] as empty.
  * algo: BEVGEN_ALGO_TILED          one binning pass into per-tile record bins; per 28.8 KB tile one CTA builds the tile
  *                                  in shared memory (warp-aggregated atomicMax) and writes it with ONE TMA bulk store
  *                                  [default of the Python layer; fastest except on dense / skewed scenes]
@@ -112,6 +115,19 @@ int bevgen_lidar_bev_fused_f16(const void *pts_h4, const int32_t *sweep_offsets,
                                const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,
                                float *out, void *workspace, size_t workspace_bytes, int algo,
                                bevgen_stream_t stream);
+
+/* same with the points in AV2's on-disk COLUMN form -- what dataset.py:311 reads from each sweep's feather file: x, y, z as
+ * float16 arrays and intensity as a uint8 array (7 B per point, no row interleaving on the host: the Arrow column buffers can
+ * be copied as they are).  Sweeps are concatenated inside each column and share sweep_offsets.  Each column pointer must be
+ * 16-byte aligned and readable up to the next multiple of 8 rows past total_points (threads read whole 8-row vectors; the
+ * padding rows are never used as points).  fp16 -> fp64 and uint8 -> fp32 are exact, so the result equals the reference's
+ * on the same values (dataset.py:320-321 widens exactly these dtypes). */
+int bevgen_lidar_bev_fused_cols(const void *x_f16, const void *y_f16, const void *z_f16, const uint8_t *intensity_u8,
+                                const int32_t *sweep_offsets, const double *rel_tf,
+                                int B, int S, int64_t total_points, int max_sweep_points,
+                                const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,
+                                float *out, void *workspace, size_t workspace_bytes, int algo,
+                                bevgen_stream_t stream);
 
 int bevgen_lidar_bev_ego_f64(const double *pts3, const float *intensity, const int32_t *sweep_offsets,
                              int B, int S, int64_t total_points, int max_sweep_points,
@@ -189,6 +205,13 @@ int bevgen_lidar_bev_augmented(const void *pts, int pts_f16, const int32_t *swee
                                int B, int S, int64_t total_points, int max_sweep_points,
                                const bevgen_aug_params *params, const bevgen_aug_params *params_host,
                                float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
+
+/* bevgen_lidar_bev_augmented on AV2 column arrays (see bevgen_lidar_bev_fused_cols for the layout rules) */
+int bevgen_lidar_bev_augmented_cols(const void *x_f16, const void *y_f16, const void *z_f16, const uint8_t *intensity_u8,
+                                    const int32_t *sweep_offsets, const double *rel_tf,
+                                    int B, int S, int64_t total_points, int max_sweep_points,
+                                    const bevgen_aug_params *params, const bevgen_aug_params *params_host,
+                                    float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
 
 /* rasterize_map_ego_centric followed by the image part of augment_bev (utils.py:508-511) on the 9 map channels, per-frame
  * parameters as in bevgen_augment (device copy + host copy): frames that neither rotate nor scale get flip / dropout

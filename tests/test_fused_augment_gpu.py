@@ -207,3 +207,21 @@ def test_repeated_runs_are_bit_identical_at_full_size(bg):
         assert torch.equal(out, first)
     dense = bg.augment_grid(bg.lidar_bev_from_sweeps(pts, off, tf, 4, 10, max_sweep_points=fb.max_sweep_points), aug)
     assert torch.equal(first, dense)
+
+
+def test_fused_augmentation_on_av2_columns(bg, co):
+    """generation fused with rotate / scale from AV2 column input == the float32 row input on the same values"""
+    frames = [bg.synthetic.quantize_f16(bg.synthetic.frame_c2(300 + i, n=6_001)) for i in range(4)]
+    aug = [bg.AugParams(angle_deg=7.5), bg.AugParams(flip=True, scale=0.97), bg.AugParams(angle_deg=-11.0, scale=1.04, rects=[(10, 20, 30, 40)]),
+           bg.AugParams(flip=True, rects=[(100, 300, 25, 45)])]
+    rows = bg.FrameBatch.pack(frames, 10)
+    cols = bg.FrameBatch.pack(frames, 10, points_dtype="av2")
+    gen = bg.BevGenerator()
+    a = gen.generate(rows, aug, with_map=False)["lidar_bev"].clone()
+    b = gen.generate(cols, aug, with_map=False)["lidar_bev"]
+    assert torch.equal(a, b)
+    f = frames[2]
+    g = co.lidar_bev_fused(f.points4, f.sweep_offsets, f.rel_tf, 10)
+    g = np.ascontiguousarray(co.scale(co.rotate(g, -11.0), 1.04)).copy()
+    co.dropout(g, [(10, 20, 30, 40)])
+    assert np.array_equal(b[2].cpu().numpy(), g)

@@ -212,3 +212,31 @@ def test_reference_signature_results_are_independent_arrays(bg):
     del a
     c = bg.create_intentnet_lidar_bev(pts, inten)
     assert t[0, 0, 0] == 123.0 and c[0, 0, 0] != 123.0
+
+
+@pytest.mark.parametrize("algo", [0, 1, 2])
+def test_av2_column_points(bg, co, algo):
+    """AV2's on-disk columns (float16 x,y,z + uint8 intensity, 7 B/point, dataset.py:311-321): identical to the oracle on
+    the same values; sweeps of odd lengths start at unaligned rows (the kernels read aligned 8-row vectors and mask),
+    empty and missing sweeps included."""
+    S = 10
+    frames = [bg.synthetic.quantize_f16(f) for f in
+              (bg.synthetic.frame_c2(80, n=4_001), bg.synthetic.frame_c1(2, n=777), bg.synthetic.frame_c4(1, n=3_003),
+               bg.synthetic.frame_c2(81, n=1, S=3), bg.synthetic.frame_c2(82, n=9_000))]
+    want = _oracle_frames(co, frames, S)
+    fb = bg.FrameBatch.pack(frames, S, points_dtype="av2")
+    assert fb.points_format == "av2" and fb.point_bytes == 7 and fb.num_points == sum(f.num_points for f in frames)
+    assert fb.h2d_bytes < 0.46 * bg.FrameBatch.pack(frames, S).h2d_bytes
+    got = bg.BevGenerator(algo=algo).generate(fb, with_map=False)["lidar_bev"].cpu().numpy()
+    assert np.array_equal(got, want)
+    # direct call on host columns; sub-range of frames (absolute CSR offsets, pointer offset of the offsets only)
+    pc = fb.points4
+    off = fb.sweep_offsets.numpy()
+    got2 = bg.lidar_bev_from_sweeps(pc, off[2 * S:5 * S + 1], fb.rel_tf.numpy()[2 * S:5 * S], 3, S, algo=algo).cpu().numpy()
+    assert np.array_equal(got2, want[2:5])
+    with pytest.raises(ValueError):
+        bg.FrameBatch.pack([bg.synthetic.frame_c2(3, n=100)], S, points_dtype="av2")         # not fp16-representable
+    f = bg.synthetic.quantize_f16(bg.synthetic.frame_c2(3, n=100))
+    f.points4[5, 3] = 0.5
+    with pytest.raises(ValueError):
+        bg.FrameBatch.pack([f], S, points_dtype="av2")                                       # intensity not a uint8 value

@@ -101,3 +101,56 @@ def test_feather_to_device_grid(bg, tmp_path):
     want = npp.lidar_bev(pl, il)
     got = bg.BevGenerator().generate(bg.FrameBatch.pack([fr], 10), with_map=False)["lidar_bev"][0]
     assert torch.equal(got.cpu(), torch.from_numpy(want))
+
+
+def test_column_layout_matches_row_layout(bg, tmp_path, capsys):
+    """layout="columns": AV2's stored columns, no interleave -- same points, same skip rules, 7 B/point when packed"""
+    ts, poses = _write_log(tmp_path, bg)
+    bg.sweep_io.clear_cache()
+    rows = bg.sweep_io.load_frame(tmp_path, ts, ts[-1], poses)
+    cols = bg.sweep_io.load_frame(tmp_path, ts, ts[-1], poses, layout="columns")
+    assert cols.points4 is None and [c.dtype for c in cols.columns] == [np.float16] * 3 + [np.uint8]
+    assert np.array_equal(cols.sweep_offsets, rows.sweep_offsets) and np.array_equal(cols.sweep_poses, rows.sweep_poses)
+    assert np.array_equal(np.stack([c.astype(np.float32) for c in cols.columns], 1), rows.points4.astype(np.float32))
+    fb = bg.FrameBatch.pack([cols], 10)                       # auto: frames that carry columns are packed as columns
+    assert fb.points_format == "av2" and fb.num_points == rows.points4.shape[0]
+    assert np.array_equal(fb.points4.to_points4(), rows.points4.astype(np.float32))
+    assert fb.h2d_bytes < bg.FrameBatch.pack([rows], 10).h2d_bytes
+    # a log stored as float32 is not columnar: the frame falls back to rows
+    sub = tmp_path / "f32"
+    sub.mkdir()
+    ts2, poses2 = _write_log(sub, bg, n=50, S=3, dtype=np.float32)
+    fr = bg.sweep_io.load_frame(sub, ts2, ts2[-1], poses2, layout="columns")
+    assert fr.columns is None and fr.points4.dtype == np.float32
+    with pytest.raises(ValueError):
+        bg.sweep_io.load_frame(tmp_path, ts, ts[-1], poses, layout="nope")
+
+
+def test_point_columns_roundtrip(bg):
+    rng = np.random.default_rng(0)
+    n = 1003
+    x, y, z = (rng.normal(0, 30, n).astype(np.float16) for _ in range(3))
+    i = rng.integers(0, 256, n).astype(np.uint8)
+    pc = bg.PointColumns.from_arrays(x, y, z, i, pinned=False)
+    assert pc.n == n and pc.stride == 1008 and pc.nbytes == 7 * 1008
+    assert np.array_equal(pc.to_points4(), np.stack([x, y, z, i], 1).astype(np.float32))
+    pc2 = bg.PointColumns.from_points4(pc.to_points4(), pinned=False)
+    assert bytes(pc2.buf.numpy()) == bytes(pc.buf.numpy())
+    with pytest.raises(ValueError):
+        bg.PointColumns.from_arrays(x.astype(np.float32) + 1e-3, y, z, i, pinned=False)
+    with pytest.raises(ValueError):
+        bg.PointColumns.from_arrays(x, y, z, i.astype(np.float32) + 0.5, pinned=False)
+    assert bg.PointColumns.from_arrays([], [], [], [], pinned=False).stride == 8
+
+
+@pytest.mark.gpu
+def test_feather_columns_to_device_grid(bg, tmp_path):
+    from oracle import numpy_port as npp
+    import torch
+    ts, poses = _write_log(tmp_path, bg)
+    bg.sweep_io.clear_cache()
+    fr = bg.sweep_io.load_frame(tmp_path, ts, ts[-1], poses, layout="columns")
+    pl, il = _reference_loop(tmp_path, ts, poses, ts[-1])
+    want = npp.lidar_bev(pl, il)
+    got = bg.BevGenerator().generate(bg.FrameBatch.pack([fr], 10), with_map=False)["lidar_bev"][0]
+    assert torch.equal(got.cpu(), torch.from_numpy(want))

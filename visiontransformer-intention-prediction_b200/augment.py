@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .bev_ops import _dev, _device_of, _ptr, _require_cuda, _stream_ptr, to_numpy_fresh, workspace
+from .bev_ops import PointColumns, _dev, _device_of, _ptr, _require_cuda, _stream_ptr, to_numpy_fresh, workspace
 from .constants import GRID_HEIGHT_PX, GRID_WIDTH_PX, INTENTIONS_MAP
 
 _CV_PI = 3.1415926535897932384626433832795
@@ -170,12 +170,14 @@ def lidar_bev_augmented(points4: torch.Tensor, sweep_offsets: torch.Tensor, rel_
     B, S = int(num_frames), int(num_sweeps)
     if len(params) != B:
         raise ValueError("one AugParams per frame")
-    if points4.dim() != 2 or points4.shape[1] != 4 or points4.dtype not in (torch.float32, torch.float16) or not points4.is_cuda:
-        raise ValueError("points4 must be a CUDA tensor [N,4] float32 or float16")
+    cols = isinstance(points4, PointColumns)
+    if not points4.is_cuda or (not cols and (points4.dim() != 2 or points4.shape[1] != 4
+                                             or points4.dtype not in (torch.float32, torch.float16))):
+        raise ValueError("points4 must be a CUDA tensor [N,4] float32 or float16, or a device-resident PointColumns")
     device = points4.device
     shape = (B, S * 29, GRID_HEIGHT_PX, GRID_WIDTH_PX)
     with torch.cuda.device(device):
-        pts = points4.contiguous()
+        pts = points4 if cols else points4.contiguous()
         off = _dev(sweep_offsets, torch.int32, device)
         tf = _dev(rel_tf, torch.float64, device).reshape(-1, 16)
         if off.numel() != B * S + 1 or tf.shape[0] != B * S:
@@ -187,12 +189,17 @@ def lidar_bev_augmented(points4: torch.Tensor, sweep_offsets: torch.Tensor, rel_
         hparams = pack_params(params) if packed is None else packed
         dparams = _dev(hparams, torch.uint8, device)
         L = _native.lib()
-        n = int(pts.shape[0])
+        n = pts.n if cols else int(pts.shape[0])
         wbytes = int(L.bevgen_lidar_aug_workspace_bytes(n, B, S, sum(1 for p in params if p.needs_gather)))
         ws = workspace.get("lidar", wbytes, device)
-        rc = L.bevgen_lidar_bev_augmented(_ptr(pts), 1 if pts.dtype == torch.float16 else 0, _ptr(off), _ptr(tf), B, S, n,
-                                          int(max_sweep_points), _ptr(dparams), C.c_void_p(hparams.ctypes.data), _ptr(out),
-                                          _ptr(ws), wbytes, _stream_ptr())
+        if cols:
+            rc = L.bevgen_lidar_bev_augmented_cols(*pts.ptrs(), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
+                                                   _ptr(dparams), C.c_void_p(hparams.ctypes.data), _ptr(out), _ptr(ws), wbytes,
+                                                   _stream_ptr())
+        else:
+            rc = L.bevgen_lidar_bev_augmented(_ptr(pts), 1 if pts.dtype == torch.float16 else 0, _ptr(off), _ptr(tf), B, S, n,
+                                              int(max_sweep_points), _ptr(dparams), C.c_void_p(hparams.ctypes.data), _ptr(out),
+                                              _ptr(ws), wbytes, _stream_ptr())
     _native.check(rc, "bevgen_lidar_bev_augmented")
     return out
 

@@ -79,6 +79,82 @@ def _dev(a, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device, non_blocking=True)
 
 
+class PointColumns:
+    """A batch of sweeps in AV2's on-disk column form (dataset.py:311 reads exactly these columns): ``x``, ``y``, ``z``
+    float16 and ``intensity`` uint8, sweeps concatenated inside each column -- 7 bytes per point instead of the 16 of a
+    float32 ``[N,4]`` row array, and no interleaving work on the host (Arrow column buffers are copied as they are).
+
+    Held as ONE uint8 buffer ``[7 * stride]`` = x | y | z | intensity (``stride`` = rows per column, a multiple of 8 so
+    every column starts 16-byte aligned and whole 8-row vectors are readable), so a batch is one host->device copy."""
+
+    def __init__(self, buf: torch.Tensor, n: int, stride: int) -> None:
+        if buf.dtype != torch.uint8 or buf.dim() != 1 or stride % 8 or buf.numel() != 7 * stride or not 0 <= n <= stride:
+            raise ValueError("PointColumns: uint8 buffer of 7 * stride bytes, stride a multiple of 8, n <= stride")
+        self.buf, self.n, self.stride = buf, int(n), int(stride)
+
+    @staticmethod
+    def stride_for(n: int) -> int:
+        return max(8, (int(n) + 7) // 8 * 8)
+
+    @classmethod
+    def from_arrays(cls, x, y, z, intensity, pinned: bool = True) -> "PointColumns":
+        """Pack host columns (lossless: raises when a value is not representable in float16 / uint8)."""
+        cols = [np.asarray(c).reshape(-1) for c in (x, y, z, intensity)]
+        n = cols[0].shape[0]
+        if any(c.shape[0] != n for c in cols):
+            raise ValueError("x, y, z, intensity must have the same length")
+        stride = cls.stride_for(n)
+        buf = torch.zeros(7 * stride, dtype=torch.uint8)
+        if pinned and torch.cuda.is_available():
+            buf = buf.pin_memory()
+        host = buf.numpy()
+        for k, c in enumerate(cols[:3]):
+            h = c if c.dtype == np.float16 else c.astype(np.float16)
+            if h is not c and not np.array_equal(h.astype(np.float64), c.astype(np.float64), equal_nan=True):
+                raise ValueError("coordinates are not exactly representable in float16; use the float32 row format")
+            host[2 * k * stride:2 * k * stride + 2 * n].view(np.float16)[:] = h
+        i8 = cols[3] if cols[3].dtype == np.uint8 else cols[3].astype(np.uint8)
+        if i8 is not cols[3] and not np.array_equal(i8.astype(np.float64), cols[3].astype(np.float64)):
+            raise ValueError("intensities are not integers in [0, 255]; use the float32 row format")
+        host[6 * stride:6 * stride + n] = i8
+        return cls(buf, n, stride)
+
+    @classmethod
+    def from_points4(cls, points4: np.ndarray, pinned: bool = True) -> "PointColumns":
+        p = np.asarray(points4).reshape(-1, 4)
+        return cls.from_arrays(p[:, 0], p[:, 1], p[:, 2], p[:, 3], pinned=pinned)
+
+    # -- tensor-like surface used by the pipeline
+    @property
+    def device(self) -> torch.device:
+        return self.buf.device
+
+    @property
+    def is_cuda(self) -> bool:
+        return self.buf.is_cuda
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.buf.numel())
+
+    def to(self, device, non_blocking: bool = False) -> "PointColumns":
+        return PointColumns(self.buf.to(device, non_blocking=non_blocking), self.n, self.stride)
+
+    def record_stream(self, stream) -> None:
+        self.buf.record_stream(stream)
+
+    def ptrs(self):
+        b = self.buf.data_ptr()
+        return tuple(C.c_void_p(b + k * self.stride) for k in (0, 2, 4, 6))
+
+    def to_points4(self) -> np.ndarray:
+        """float32 [n,4] rows (host copy; for tests and the CPU oracle)."""
+        host = self.buf.cpu().numpy()
+        s, n = self.stride, self.n
+        xyz = [host[2 * k * s:2 * k * s + 2 * n].view(np.float16).astype(np.float32) for k in range(3)]
+        return np.stack(xyz + [host[6 * s:6 * s + n].astype(np.float32)], axis=1)
+
+
 class _Workspace:
     """Grow-only scratch buffer per (purpose, device, CUDA stream); kernels never allocate.
 
@@ -184,13 +260,14 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
                           out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
     """Fused dataset.py:339-340 + utils.py:62-106 for ``num_frames`` frames.
 
-    points4        float32 (16 B/pt) or float16 (8 B/pt, AV2's stored precision) [N,4]  (x, y, z, intensity) in each
-                   sweep's own frame, sweeps concatenated
+    points4        float32 (16 B/pt) or float16 (8 B/pt) [N,4]  (x, y, z, intensity) in each sweep's own frame, sweeps
+                   concatenated -- or a ``PointColumns`` (AV2's on-disk columns: float16 x,y,z + uint8 intensity, 7 B/pt)
     sweep_offsets  int32 [B*S+1]  CSR offsets; an empty range = missing sweep (its 29 channels stay 0)
     rel_tf         float64 [B*S,4,4]  ego_SE3_world @ sweep_SE3 (pose.sweep_rel_transforms)
     returns        float32 CUDA tensor [B, S*29, 400, 720]
     """
-    device = _device_of(points4, sweep_offsets, rel_tf, out)
+    cols = points4 if isinstance(points4, PointColumns) else None
+    device = _device_of(cols.buf if cols is not None else points4, sweep_offsets, rel_tf, out)
     B, S = int(num_frames), int(num_sweeps)
     host_off = None
     if not isinstance(sweep_offsets, torch.Tensor) or not sweep_offsets.is_cuda:
@@ -199,14 +276,18 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
     half = (isinstance(points4, torch.Tensor) and points4.dtype == torch.float16) or \
            (isinstance(points4, np.ndarray) and points4.dtype == np.float16)
     with torch.cuda.device(device):
-        pts = _dev(points4, torch.float16 if half else torch.float32, device)
         off = _dev(sweep_offsets, torch.int32, device)
         tf = _dev(rel_tf, torch.float64, device).reshape(-1, 16)
-        if pts.dim() != 2 or pts.shape[1] != 4:
-            raise ValueError("points4 must be [N,4] float32 or float16 (x,y,z,intensity)")
+        if cols is not None:
+            pts = cols if cols.is_cuda else cols.to(device, non_blocking=True)
+            n = pts.n
+        else:
+            pts = _dev(points4, torch.float16 if half else torch.float32, device)
+            if pts.dim() != 2 or pts.shape[1] != 4:
+                raise ValueError("points4 must be [N,4] float32 or float16 (x,y,z,intensity), or a PointColumns")
+            n = int(pts.shape[0])
         if off.numel() != B * S + 1 or tf.shape[0] != B * S:
             raise ValueError("sweep_offsets must have B*S+1 entries and rel_tf B*S matrices")
-        n = int(pts.shape[0])
         if host_off is not None:
             max_sweep_points = _check_offsets(host_off, n, max_sweep_points)
         elif max_sweep_points is None:
@@ -223,9 +304,13 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
         if algo == ALGO_TILED:
             wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
             ws = workspace.get("lidar", wbytes, device)
-        fn = L.bevgen_lidar_bev_fused_f16 if half else L.bevgen_lidar_bev_fused
-        rc = fn(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
-                _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
+        if cols is not None:
+            rc = L.bevgen_lidar_bev_fused_cols(*pts.ptrs(), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
+                                               _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
+        else:
+            fn = L.bevgen_lidar_bev_fused_f16 if half else L.bevgen_lidar_bev_fused
+            rc = fn(_ptr(pts), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
+                    _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
     _native.check(rc, "bevgen_lidar_bev_fused")
     return out
 

@@ -32,6 +32,9 @@ constexpr int kBinChunk = kBinThreads * kBinItems;     // points per CTA
 constexpr int kRowBytes = kW * 4;                      // 2 880 (multiple of 16: bulk-copy legal)
 
 struct LidarIn {
+    // MODE 3: AV2 sweep columns as stored on disk (dataset.py:311 reads x, y, z float16 + intensity uint8): four arrays,
+    // sweeps concatenated inside each, 7 B / point, each 16-byte aligned and readable up to the next multiple of 8 rows
+    const __half* col_x = nullptr; const __half* col_y = nullptr; const __half* col_z = nullptr; const uint8_t* col_i = nullptr;
     const uint2* pts_h4;       // MODE 2: 4 x fp16 (x, y, z, intensity) = 8 B / point (AV2's on-disk precision)
     const float4* pts4;        // MODE 0
     const double* rel_tf;      // MODE 0: [B*S,16]
@@ -56,6 +59,15 @@ __device__ __forceinline__ void sweep_range(const LidarIn& in, int bs, int& beg,
     beg = beg < 0 ? 0 : beg;
     end = end > in.n_points ? in.n_points : end;
     if (beg < off0 || off0 < 0) end = beg;
+}
+
+inline LidarIn make_in(const uint2* h4, const float4* p4, const double* rel_tf, const double* p3, const float* inten,
+                       const int32_t* off, const uint8_t* flip, const int32_t* rects, const int32_t* nrects, int S,
+                       const bevgen_aug_params* aug = nullptr) {
+    LidarIn in;
+    in.pts_h4 = h4; in.pts4 = p4; in.rel_tf = rel_tf; in.pts3 = p3; in.intensity = inten; in.sweep_off = off;
+    in.flip = flip; in.rects = rects; in.nrects = nrects; in.S = S; in.aug = aug;
+    return in;
 }
 
 // Raw point as loaded from HBM.  Loads are issued for ALL of a thread's items before the first use, so
@@ -88,6 +100,32 @@ template <>
 __device__ __forceinline__ RawPoint<2> load_point<2>(const LidarIn& in, long long i, bool in_range) {
     RawPoint<2> r;
     r.h = in_range ? __ldcs(in.pts_h4 + i) : make_uint2(0u, 0u);               // streaming 8 B load, fully coalesced
+    return r;
+}
+
+// MODE 3: one thread takes 8 CONSECUTIVE rows of the four columns: three 16 B loads + one 8 B load per 8 points (the
+// row-interleaved formats issue one load per point), a warp reads 512 contiguous bytes of each fp16 column.  `i8` is a
+// multiple of 8, so every vector is aligned; rows outside the sweep's [beg, end) are masked by the caller.
+struct ColGroup { uint4 x, y, z; uint2 v; };
+__device__ __forceinline__ ColGroup load_cols(const LidarIn& in, uint32_t i8, bool in_range) {
+    ColGroup g;
+    g.x = g.y = g.z = make_uint4(0u, 0u, 0u, 0u); g.v = make_uint2(0u, 0u);
+    if (in_range) {
+        g.x = __ldcs(reinterpret_cast<const uint4*>(in.col_x + i8));
+        g.y = __ldcs(reinterpret_cast<const uint4*>(in.col_y + i8));
+        g.z = __ldcs(reinterpret_cast<const uint4*>(in.col_z + i8));
+        g.v = __ldcs(reinterpret_cast<const uint2*>(in.col_i + i8));
+    }
+    return g;
+}
+__device__ __forceinline__ float half_at(const uint4& q, int u) {          // u compile-time after unrolling
+    const uint32_t w = u < 2 ? q.x : (u < 4 ? q.y : (u < 6 ? q.z : q.w));
+    return __half2float(__ushort_as_half((unsigned short)((u & 1) ? (w >> 16) : (w & 0xFFFFu))));
+}
+__device__ __forceinline__ RawPoint<0> col_point(const ColGroup& g, int u) {
+    RawPoint<0> r;          // fp16 -> fp32 and uint8 -> fp32 are exact: same values the reference widens to float64 / float32
+    const uint32_t w = u < 4 ? g.v.x : g.v.y;
+    r.p = make_float4(half_at(g.x, u), half_at(g.y, u), half_at(g.z, u), (float)((w >> (8 * (u & 3))) & 0xFFu));
     return r;
 }
 
@@ -191,7 +229,8 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
     const int bs = bs0 + blockIdx.y, b = bs / in.S, tid = threadIdx.x;
     int beg, end;
     sweep_range(in, bs, beg, end);
-    if ((long long)beg + (long long)blockIdx.x * kAggChunk >= end) return;
+    const uint32_t org = MODE == 3 ? ((uint32_t)beg & ~7u) : (uint32_t)beg;   // column vectors are 8-row aligned
+    if ((long long)org + (long long)blockIdx.x * kAggChunk >= end) return;
     __shared__ double sT[12];
     __shared__ int sRect[kMaxRects * 4];
     __shared__ uint32_t s_spill_n, s_spill_base;
@@ -200,10 +239,37 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
     // The grid's x extent comes from the caller's max_sweep_points (a sizing hint): a sweep longer than that is still
     // binned completely, its CTAs walk the remaining chunks (normally this loop runs once).
 #pragma unroll 1
-    for (uint32_t chunk0 = (uint32_t)beg + blockIdx.x * (uint32_t)kAggChunk; chunk0 < (uint32_t)end; chunk0 += gridDim.x * (uint32_t)kAggChunk) {
+    for (uint32_t chunk0 = org + blockIdx.x * (uint32_t)kAggChunk; chunk0 < (uint32_t)end; chunk0 += gridDim.x * (uint32_t)kAggChunk) {
     for (int i = tid; i < kTilesPerSweep; i += kAggThreads) hist[i] = 0;
     __syncthreads();
     // phase 1: records + per-tile rank inside the CTA (shared atomics)
+    auto emit = [&](int k, bool ok, const Voxel& v) {
+        uint32_t word = 0xFFFFFFFFu;
+        if (ok) {
+            const uint32_t band = (uint32_t)v.py / kFillRows;
+            const uint32_t bin = (uint32_t)v.zb * (kH / kFillRows) + band;
+            const uint32_t tcell = ((uint32_t)v.py - band * kFillRows) * kW + (uint32_t)v.px;
+            word = (bin << 13) | tcell;
+            rank[k] = (uint16_t)atomicAdd(&hist[bin], 1u);
+        }
+        recs[k] = make_uint2(word, v.bits);
+    };
+    if constexpr (MODE == 3) {
+        // 8 consecutive rows per thread and group: 56 B per thread in flight (4 vector loads), 2 x 512 threads per SM
+#pragma unroll 1
+        for (int g = 0; g < kAggItems / 8; ++g) {
+            const uint32_t i8 = chunk0 + (uint32_t)((g * kAggThreads + tid) * 8);
+            const ColGroup grp = load_cols(in, i8, i8 < (uint32_t)end);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t i = i8 + (uint32_t)u;
+                Voxel v;
+                v.bits = 0;
+                const bool ok = i >= (uint32_t)beg && i < (uint32_t)end && point_voxel<0>(col_point(grp, u), sT, flip, sRect, nrect, v);
+                emit((g * 8 + u) * kAggThreads + tid, ok, v);       // slot index: conflict-free, any bijection works
+            }
+        }
+    } else {
 #pragma unroll 1
     for (int g = 0; g < kAggItems; g += 4) {
         RawPoint<MODE> raw[4];
@@ -219,17 +285,9 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
             Voxel v;
             v.bits = 0;
             const bool ok = (i < (uint32_t)end) && point_voxel<MODE>(raw[u], sT, flip, sRect, nrect, v);
-            uint32_t word = 0xFFFFFFFFu;
-            if (ok) {
-                const uint32_t band = (uint32_t)v.py / kFillRows;
-                const uint32_t bin = (uint32_t)v.zb * (kH / kFillRows) + band;
-                const uint32_t tcell = ((uint32_t)v.py - band * kFillRows) * kW + (uint32_t)v.px;
-                word = (bin << 13) | tcell;
-                rank[k] = (uint16_t)atomicAdd(&hist[bin], 1u);
-            }
-            const uint32_t bits = v.bits;
-            recs[k] = make_uint2(word, bits);
+            emit(k, ok, v);
         }
+    }
     }
     __syncthreads();
     // phase 2: one global claim per touched tile (all of a thread's claims are in flight together)
@@ -362,32 +420,53 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint
     const int bs = bs0 + blockIdx.y, b = bs / in.S;
     int beg, end;
     sweep_range(in, bs, beg, end);
-    if ((long long)beg + (long long)blockIdx.x * kBinChunk >= end) return;
+    if ((long long)(MODE == 3 ? (beg & ~7) : beg) + (long long)blockIdx.x * kBinChunk >= end) return;
     __shared__ double sT[12];
     __shared__ int sRect[kMaxRects * 4];
     int nrect; bool flip;
     load_frame_consts(in, bs, b, MODE, sT, sRect, nrect, flip);
     __syncthreads();
     // grid x extent = the caller's max_sweep_points hint; longer sweeps are still covered (loop normally runs once)
+    const uint32_t org = MODE == 3 ? ((uint32_t)beg & ~7u) : (uint32_t)beg;
 #pragma unroll 1
-    for (long long chunk0 = (long long)beg + (long long)blockIdx.x * kBinChunk; chunk0 < end; chunk0 += (long long)gridDim.x * kBinChunk) {
+    for (uint32_t chunk0 = org + blockIdx.x * (uint32_t)kBinChunk; chunk0 < (uint32_t)end; chunk0 += gridDim.x * (uint32_t)kBinChunk) {
+    uint32_t* addr[kBinItems];
+    uint32_t val[kBinItems];
+    if constexpr (MODE == 3) {
+        static_assert(kBinItems == 4, "two threads share one 8-row column group");
+        // thread t takes rows [4t, 4t+4) of the chunk: the 16 B / 8 B vectors are fetched by the pair of threads that share
+        // them (the second fetch hits L1), which keeps the chunk geometry of the row formats
+        const uint32_t i8 = chunk0 + (uint32_t)(threadIdx.x >> 1) * 8u;
+        const ColGroup grp = load_cols(in, i8, i8 < (uint32_t)end);
+        const int h = (threadIdx.x & 1) * 4;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const uint32_t i = i8 + (uint32_t)(h + it);
+            Voxel v;
+            addr[it] = nullptr; val[it] = 0;
+            const RawPoint<0> rp = h ? col_point(grp, 4 + it) : col_point(grp, it);
+            if (i >= (uint32_t)beg && i < (uint32_t)end && point_voxel<0>(rp, sT, flip, sRect, nrect, v)) {
+                addr[it] = out + ((size_t)(bs * kZ + v.zb) * kH + v.py) * kW + v.px;
+                val[it] = v.bits;
+            }
+        }
+    } else {
     RawPoint<MODE> raw[kBinItems];
 #pragma unroll
     for (int it = 0; it < kBinItems; ++it) {
-        const long long i = chunk0 + it * kBinThreads + threadIdx.x;
-        raw[it] = load_point<MODE>(in, i, i < end);
+        const uint32_t i = chunk0 + (uint32_t)(it * kBinThreads + threadIdx.x);
+        raw[it] = load_point<MODE>(in, (long long)i, i < (uint32_t)end);
     }
-    uint32_t* addr[kBinItems];
-    uint32_t val[kBinItems];
 #pragma unroll
     for (int it = 0; it < kBinItems; ++it) {
-        const long long i = chunk0 + it * kBinThreads + threadIdx.x;
+        const uint32_t i = chunk0 + (uint32_t)(it * kBinThreads + threadIdx.x);
         Voxel v;
         addr[it] = nullptr; val[it] = 0;
-        if (i < end && point_voxel<MODE>(raw[it], sT, flip, sRect, nrect, v)) {
+        if (i < (uint32_t)end && point_voxel<MODE>(raw[it], sT, flip, sRect, nrect, v)) {
             addr[it] = out + ((size_t)(bs * kZ + v.zb) * kH + v.py) * kW + v.px;
             val[it] = v.bits;
         }
+    }
     }
 #pragma unroll
     for (int it = 0; it < kBinItems; ++it)
@@ -437,7 +516,8 @@ int launch_lidar(LidarIn in, int B, int S, long long total_points, int max_sweep
     if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;      // TMA bulk stores need 16 B alignment
     const size_t ntiles = (size_t)B * S * kTilesPerSweep;
     if (ntiles > 0x7FFFFFFFull) return BEVGEN_E_UNSUPPORTED;
-    const int chunks = max_sweep_points > 0 ? (max_sweep_points + kBinChunk - 1) / kBinChunk : 0;
+    const int pad = MODE == 3 ? 7 : 0;         // column vectors are 8-row aligned: a sweep's first chunk may start up to 7 rows early
+    const int chunks = max_sweep_points > 0 ? (max_sweep_points + pad + kBinChunk - 1) / kBinChunk : 0;
     const dim3 bin_grid(chunks > 0 ? chunks : 1, B * S);
     if (bin_grid.y > 65535u) return BEVGEN_E_UNSUPPORTED;
 
@@ -471,7 +551,7 @@ int launch_lidar(LidarIn in, int B, int S, long long total_points, int max_sweep
         // (Measured: splitting the batch into frame groups, with or without overlapping the binning of group g+1 with
         //  the stores of group g on a second stream, is slower than these three whole-batch launches.)
         if (chunks > 0) {
-            const dim3 agg_grid((max_sweep_points + kAggChunk - 1) / kAggChunk, B * S);
+            const dim3 agg_grid((max_sweep_points + pad + kAggChunk - 1) / kAggChunk, B * S);
             BEVGEN_LAUNCH("k_bin_fixed", st, k_bin_fixed<MODE><<<agg_grid, kAggThreads, kAggSmem, st>>>(in, cnt, bins, ovf_cnt, ovf, 0));
         }
         BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<(unsigned)ntiles, 128, kFillBytes, st>>>(cnt, bins, out, 0u));
@@ -519,7 +599,7 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
     BEVGEN_DYN_SMEM((k_tile_aug<true, true>), (AugTileCfg<true, true>::kSmem));
     const bool have_points = max_sweep_points > 0;
     if (have_points) {
-        const dim3 agg_grid((max_sweep_points + kAggChunk - 1) / kAggChunk, B * S);
+        const dim3 agg_grid((max_sweep_points + (MODE == 3 ? 7 : 0) + kAggChunk - 1) / kAggChunk, B * S);
         BEVGEN_LAUNCH("k_bin_fixed", st, k_bin_fixed<MODE><<<agg_grid, kAggThreads, kAggSmem, st>>>(in, cnt, bins, ovf_cnt, ovf, 0));
     }
     auto cls_of = [&](int b) { return (params_host[b].do_rotate != 0 ? 1 : 0) | (params_host[b].do_scale != 0 ? 2 : 0); };
@@ -609,8 +689,8 @@ extern "C" int bevgen_lidar_bev_augmented(const void* pts, int pts_f16, const in
                                           void* workspace, size_t workspace_bytes, bevgen_stream_t stream) {
     if (total_points > 0 && (!pts || !rel_tf)) return BEVGEN_E_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(pts) & (pts_f16 ? 7u : 15u)) != 0) return BEVGEN_E_INVALID_ARG;
-    LidarIn in{pts_f16 ? static_cast<const uint2*>(pts) : nullptr, pts_f16 ? nullptr : static_cast<const float4*>(pts), rel_tf,
-               nullptr, nullptr, sweep_offsets, nullptr, nullptr, nullptr, S, params};
+    LidarIn in = make_in(pts_f16 ? static_cast<const uint2*>(pts) : nullptr, pts_f16 ? nullptr : static_cast<const float4*>(pts),
+                         rel_tf, nullptr, nullptr, sweep_offsets, nullptr, nullptr, nullptr, S, params);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return pts_f16 ? launch_lidar_augmented<2>(in, B, S, total_points, max_sweep_points, params_host, out, workspace, workspace_bytes, st)
                    : launch_lidar_augmented<0>(in, B, S, total_points, max_sweep_points, params_host, out, workspace, workspace_bytes, st);
@@ -627,7 +707,7 @@ extern "C" int bevgen_lidar_bev_fused(const float* pts4, const int32_t* sweep_of
                                       size_t workspace_bytes, int algo, bevgen_stream_t stream) {
     if (total_points > 0 && (!pts4 || !rel_tf)) return BEVGEN_E_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(pts4) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
-    LidarIn in{nullptr, reinterpret_cast<const float4*>(pts4), rel_tf, nullptr, nullptr, sweep_offsets, flip, drop_rects, drop_counts, S};
+    LidarIn in = make_in(nullptr, reinterpret_cast<const float4*>(pts4), rel_tf, nullptr, nullptr, sweep_offsets, flip, drop_rects, drop_counts, S);
     return launch_lidar<0>(in, B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo,
                            static_cast<cudaStream_t>(stream));
 }
@@ -638,9 +718,50 @@ extern "C" int bevgen_lidar_bev_fused_f16(const void* pts_h4, const int32_t* swe
                                           size_t workspace_bytes, int algo, bevgen_stream_t stream) {
     if (total_points > 0 && (!pts_h4 || !rel_tf)) return BEVGEN_E_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(pts_h4) & 7u) != 0) return BEVGEN_E_INVALID_ARG;
-    LidarIn in{static_cast<const uint2*>(pts_h4), nullptr, rel_tf, nullptr, nullptr, sweep_offsets, flip, drop_rects, drop_counts, S};
+    LidarIn in = make_in(static_cast<const uint2*>(pts_h4), nullptr, rel_tf, nullptr, nullptr, sweep_offsets, flip, drop_rects, drop_counts, S);
     return launch_lidar<2>(in, B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo,
                            static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+// AV2 column arrays: 16-byte aligned (vector loads), and -- because a thread reads whole 8-row vectors -- allocated up to
+// the next multiple of 8 rows past total_points (the Python layer pads; the padding rows are never used as points).
+bool cols_ok(const void* x, const void* y, const void* z, const void* i, int64_t total_points) {
+    if (total_points == 0) return true;
+    if (!x || !y || !z || !i) return false;
+    return ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z) |
+             reinterpret_cast<uintptr_t>(i)) & 15u) == 0;
+}
+LidarIn make_cols(const void* x, const void* y, const void* z, const uint8_t* i, const double* rel_tf, const int32_t* off,
+                  const uint8_t* flip, const int32_t* rects, const int32_t* nrects, int S, const bevgen_aug_params* aug) {
+    LidarIn in = make_in(nullptr, nullptr, rel_tf, nullptr, nullptr, off, flip, rects, nrects, S, aug);
+    in.col_x = static_cast<const __half*>(x); in.col_y = static_cast<const __half*>(y); in.col_z = static_cast<const __half*>(z);
+    in.col_i = i;
+    return in;
+}
+}  // namespace
+
+extern "C" int bevgen_lidar_bev_fused_cols(const void* x_f16, const void* y_f16, const void* z_f16, const uint8_t* intensity_u8,
+                                           const int32_t* sweep_offsets, const double* rel_tf, int B, int S, int64_t total_points,
+                                           int max_sweep_points, const uint8_t* flip, const int32_t* drop_rects,
+                                           const int32_t* drop_counts, float* out, void* workspace, size_t workspace_bytes,
+                                           int algo, bevgen_stream_t stream) {
+    if (total_points > 0 && !rel_tf) return BEVGEN_E_INVALID_ARG;
+    if (!cols_ok(x_f16, y_f16, z_f16, intensity_u8, total_points)) return BEVGEN_E_INVALID_ARG;
+    return launch_lidar<3>(make_cols(x_f16, y_f16, z_f16, intensity_u8, rel_tf, sweep_offsets, flip, drop_rects, drop_counts, S, nullptr),
+                           B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bevgen_lidar_bev_augmented_cols(const void* x_f16, const void* y_f16, const void* z_f16, const uint8_t* intensity_u8,
+                                               const int32_t* sweep_offsets, const double* rel_tf, int B, int S,
+                                               int64_t total_points, int max_sweep_points, const bevgen_aug_params* params,
+                                               const bevgen_aug_params* params_host, float* out, void* workspace,
+                                               size_t workspace_bytes, bevgen_stream_t stream) {
+    if (total_points > 0 && !rel_tf) return BEVGEN_E_INVALID_ARG;
+    if (!cols_ok(x_f16, y_f16, z_f16, intensity_u8, total_points)) return BEVGEN_E_INVALID_ARG;
+    return launch_lidar_augmented<3>(make_cols(x_f16, y_f16, z_f16, intensity_u8, rel_tf, sweep_offsets, nullptr, nullptr, nullptr, S, params),
+                                     B, S, total_points, max_sweep_points, params_host, out, workspace, workspace_bytes,
+                                     static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int bevgen_lidar_bev_ego_f64(const double* pts3, const float* intensity, const int32_t* sweep_offsets, int B, int S,
@@ -648,7 +769,7 @@ extern "C" int bevgen_lidar_bev_ego_f64(const double* pts3, const float* intensi
                                         const int32_t* drop_rects, const int32_t* drop_counts, float* out, void* workspace,
                                         size_t workspace_bytes, int algo, bevgen_stream_t stream) {
     if (total_points > 0 && (!pts3 || !intensity)) return BEVGEN_E_INVALID_ARG;
-    LidarIn in{nullptr, nullptr, nullptr, pts3, intensity, sweep_offsets, flip, drop_rects, drop_counts, S};
+    LidarIn in = make_in(nullptr, nullptr, nullptr, pts3, intensity, sweep_offsets, flip, drop_rects, drop_counts, S);
     return launch_lidar<1>(in, B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo,
                            static_cast<cudaStream_t>(stream));
 }

@@ -29,7 +29,7 @@ def _pinned(arr: np.ndarray) -> torch.Tensor:
 @dataclasses.dataclass
 class FrameBatch:
     """Host-side (pinned) packed batch."""
-    points4: torch.Tensor        # float32 or float16 [N,4]
+    points4: object              # torch float32 / float16 [N,4] rows, or bev_ops.PointColumns (AV2 columns, 7 B / point)
     sweep_offsets: torch.Tensor  # int32 [B*S+1]
     rel_tf: torch.Tensor         # float64 [B*S,16]
     ego_T: torch.Tensor          # float64 [B,9]
@@ -40,17 +40,30 @@ class FrameBatch:
 
     @property
     def num_points(self) -> int:
-        return int(self.points4.shape[0])
+        return self.points4.n if isinstance(self.points4, bev_ops.PointColumns) else int(self.points4.shape[0])
+
+    @property
+    def points_format(self) -> str:
+        if isinstance(self.points4, bev_ops.PointColumns):
+            return "av2"
+        return "f16" if self.points4.dtype == torch.float16 else "f32"
+
+    @property
+    def point_bytes(self) -> int:
+        return {"av2": 7, "f16": 8, "f32": 16}[self.points_format]
 
     @property
     def h2d_bytes(self) -> int:
-        return int(self.points4.numel() * self.points4.element_size() + self.sweep_offsets.numel() * 4 + self.rel_tf.numel() * 8 + self.ego_T.numel() * 8)
+        pb = self.points4.nbytes if isinstance(self.points4, bev_ops.PointColumns) else self.points4.numel() * self.points4.element_size()
+        return int(pb + self.sweep_offsets.numel() * 4 + self.rel_tf.numel() * 8 + self.ego_T.numel() * 8)
 
     @staticmethod
     def pack(frames: Sequence, num_sweeps: int = LIDAR_SWEEPS, map_ids: Optional[Sequence[int]] = None,
              points_dtype=None) -> "FrameBatch":
-        """frames: objects with points4 [n,4] f32, sweep_offsets [s+1], sweep_poses [s,7], current_pose [7]
-        (e.g. synthetic.Frame).  Sweeps beyond ``num_sweeps`` are an error, as in the reference (utils.py:102)."""
+        """frames: objects with points4 [n,4] (or ``columns`` = (x, y, z, intensity) arrays), sweep_offsets [s+1],
+        sweep_poses [s,7], current_pose [7] (e.g. synthetic.Frame, sweep_io.SweepFrame).  Sweeps beyond ``num_sweeps`` are
+        an error, as in the reference (utils.py:102).  ``points_dtype``: np.float32 (16 B/point rows), np.float16 (8 B/point
+        rows) or "av2" (AV2's on-disk columns, 7 B/point); default = the narrowest the frames already come in."""
         B, S = len(frames), int(num_sweeps)
         counts = np.zeros((B, S), np.int64)
         rel = np.tile(np.eye(4), (B, S, 1, 1))
@@ -67,6 +80,17 @@ class FrameBatch:
         off[1:] = np.cumsum(counts.reshape(-1))
         if off[-1] >= 2 ** 31:
             raise ValueError("more than 2^31 points in one batch")
+        want_cols = (isinstance(points_dtype, str) and points_dtype == "av2") or \
+                    (points_dtype is None and B > 0 and all(getattr(f, "columns", None) is not None for f in frames))
+        if want_cols:
+            # AV2 columns: frames that carry (x, y, z, intensity) column arrays (sweep_io.load_frame(layout="columns")) are
+            # concatenated column by column -- no interleave; row frames are split (lossless or an error)
+            parts = [f.columns if getattr(f, "columns", None) is not None else tuple(np.asarray(f.points4).reshape(-1, 4)[:, k] for k in range(4))
+                     for f in frames]
+            cat = [np.concatenate([p[k] for p in parts]) if B else np.zeros(0, np.float16 if k < 3 else np.uint8) for k in range(4)]
+            ids = np.full(B, -1, np.int64) if map_ids is None else np.asarray(map_ids, np.int64)
+            return FrameBatch(bev_ops.PointColumns.from_arrays(*cat), _pinned(off.astype(np.int32)), _pinned(rel.reshape(B * S, 16)),
+                              _pinned(ego.reshape(B, 9)), ids, B, S, int(counts.max()) if B else 0)
         pts = np.concatenate([np.asarray(f.points4).reshape(-1, 4) for f in frames], 0) if B else np.zeros((0, 4), np.float32)
         if points_dtype is None:             # auto: keep fp16 when every frame already is (sweep_io.load_frame)
             points_dtype = np.float16 if (B and all(np.asarray(f.points4).dtype == np.float16 for f in frames)) else np.float32

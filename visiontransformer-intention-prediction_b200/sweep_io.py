@@ -43,7 +43,7 @@ class _SweepCache:
 
     @staticmethod
     def _size(v: Optional[np.ndarray]) -> int:
-        return 64 if v is None else int(v.nbytes) + 64
+        return int(getattr(v, "nbytes", 0)) + 64
 
     def get(self, key: str):
         with self._lock:
@@ -127,6 +127,50 @@ def decode_sweep(path, use_cache: bool = True) -> Optional[np.ndarray]:
     return out
 
 
+def decode_sweep_columns(path, use_cache: bool = True):
+    """One sweep file -> its (x, y, z, intensity) COLUMNS exactly as stored (AV2: float16, float16, float16, uint8), or
+    ``None`` for the reference's "skip this sweep" cases -- no row interleaving, no dtype conversion: the arrays are the
+    Arrow column buffers.  A readable file whose columns are not (float16 x 3, uint8) yields ``NOT_COLUMNAR``: use
+    ``decode_sweep`` for it (``load_frame`` falls back by itself)."""
+    import pyarrow as pa
+    import pyarrow.feather as feather
+    key = "cols:" + str(path)
+    if use_cache:
+        hit, val = _CACHE.get(key)
+        if hit:
+            return val
+    out = None
+    p = Path(str(path))
+    if p.is_file():
+        try:
+            table = feather.read_table(str(path), columns=_COLUMNS)
+            if table.num_rows > 0:
+                cols = tuple(table.column(c).to_numpy(zero_copy_only=False) for c in _COLUMNS)
+                columnar = all(c.dtype == np.float16 for c in cols[:3]) and cols[3].dtype == np.uint8
+                out = _Columns(cols) if columnar else NOT_COLUMNAR
+        except (pa.ArrowInvalid, OSError):
+            print(f"Warning: Corrupt LiDAR sweep file: {path}. Skipping sweep.")
+            out = None
+    if use_cache:
+        _CACHE.put(key, out)
+    return out
+
+
+NOT_COLUMNAR = "not-columnar"       # decode_sweep_columns: readable sweep, but not AV2's (float16 x 3, uint8) dtypes
+
+
+class _Columns(tuple):
+    """(x, y, z, intensity) arrays of one sweep; ``nbytes`` / ``shape`` so that the LRU can size it like an array."""
+
+    @property
+    def nbytes(self) -> int:
+        return int(sum(c.nbytes for c in self))
+
+    @property
+    def shape(self):
+        return (self[0].shape[0], 4)
+
+
 def clear_cache() -> None:
     _CACHE.clear()
 
@@ -139,6 +183,7 @@ class SweepFrame:
     sweep_poses: np.ndarray
     current_pose: np.ndarray
     gt: Optional[dict] = None
+    columns: Optional[tuple] = None      # layout="columns": (x f16, y f16, z f16, intensity u8) of all sweeps; points4 is None
 
 
 def _pose_row(ego_poses_df, ts) -> Optional[np.ndarray]:
@@ -150,11 +195,15 @@ def _pose_row(ego_poses_df, ts) -> Optional[np.ndarray]:
 
 
 def load_frame(log_dir, sweep_ts_list: Sequence[int], current_ts_ns: int, ego_poses_df, *,
-               use_cache: bool = True) -> Optional[SweepFrame]:
+               use_cache: bool = True, layout: str = "rows") -> Optional[SweepFrame]:
     """dataset.py:285-342 without the CPU transform: returns ``None`` where the reference returns ``None``
     (no current pose row :286-287, invalid current quaternion :294-296, every sweep missing :344-345).
     ``use_cache=False`` decodes every file afresh (the reference's behaviour); the default goes through the
-    byte-bounded LRU (``set_cache_bytes``)."""
+    byte-bounded LRU (``set_cache_bytes``).  ``layout="columns"`` keeps AV2's stored columns (float16 x,y,z + uint8
+    intensity, 7 B/point; ``SweepFrame.columns``) instead of interleaving them into ``[N,4]`` rows -- the frame falls back
+    to rows when a file holds other dtypes."""
+    if layout not in ("rows", "columns"):
+        raise ValueError("layout must be 'rows' or 'columns'")
     cur = _pose_row(ego_poses_df, current_ts_ns)
     if cur is None:
         return None
@@ -170,7 +219,13 @@ def load_frame(log_dir, sweep_ts_list: Sequence[int], current_ts_ns: int, ego_po
     poses[:, 6] = 1.0                                            # identity for missing sweeps (never used: empty range)
     any_sweep = False
     for s, ts in enumerate(sweep_ts_list):
-        sweep = decode_sweep(base / f"{ts}.feather", use_cache=use_cache)
+        sweep = None
+        if layout == "columns":
+            sweep = decode_sweep_columns(base / f"{ts}.feather", use_cache=use_cache)
+            if sweep is NOT_COLUMNAR:                                  # other dtypes on disk: this frame goes by rows
+                layout, sweep = "rows", decode_sweep(base / f"{ts}.feather", use_cache=use_cache)
+        else:
+            sweep = decode_sweep(base / f"{ts}.feather", use_cache=use_cache)
         if sweep is None:
             continue
         prow = _pose_row(ego_poses_df, ts)                       # dataset.py:323-326
@@ -186,7 +241,11 @@ def load_frame(log_dir, sweep_ts_list: Sequence[int], current_ts_ns: int, ego_po
         any_sweep = True
     if not any_sweep:
         return None
-    dt = np.float16 if all(p.dtype == np.float16 for p in pts) else np.float32
     off = np.zeros(S + 1, np.int32)
     off[1:] = np.cumsum(counts)
+    if layout == "columns":
+        cols = tuple(np.concatenate([p[k] for p in pts]) for k in range(4))
+        return SweepFrame(None, off, poses, cur, columns=cols)
+    pts = [np.stack([c.astype(np.float32) for c in p], 1) if isinstance(p, _Columns) else p for p in pts]
+    dt = np.float16 if all(p.dtype == np.float16 for p in pts) else np.float32
     return SweepFrame(np.concatenate([p.astype(dt, copy=False) for p in pts], 0), off, poses, cur)
