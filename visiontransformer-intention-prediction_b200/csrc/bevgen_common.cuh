@@ -1,6 +1,7 @@
 // bevgen_common.cuh -- shared constants, exact-arithmetic device helpers, PTX wrappers (sm_100a).
 #pragma once
 
+#include <cuda.h>              // CUtensorMap (types only: the encoder is looked up at run time, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -169,6 +170,18 @@ __device__ __forceinline__ void bulk_wait_read() {   // <= N groups may still be
 // order this thread's generic-proxy smem writes before later async-proxy (TMA) reads
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+
+// tiled (tensor-map) form: one instruction stores a whole [1 x rows x cols] box of a 3-D tensor from a dense smem tile
+__device__ __forceinline__ void tensor_store_3d(const CUtensorMap* map, int x, int y, int z, const void* ssrc) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(ssrc)) : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// host: tensor map over a float32 grid viewed as [planes, 400, 720] with a [1, box_rows, box_cols] box (cabi.cu)
+int make_grid_tensor_map(CUtensorMap* map, float* base, uint64_t planes, uint32_t box_cols, uint32_t box_rows);
 
 // ---- PTX wrappers: per-thread async copy global -> shared (LDGSTS), 8 bytes ---------------------
 __device__ __forceinline__ void cp_async_8(void* sdst, const void* gsrc) {

@@ -47,6 +47,33 @@ int ensure_dyn_smem(const void* kernel, int bytes) {
     return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda).
+int make_grid_tensor_map(CUtensorMap* map, float* base, uint64_t planes, uint32_t box_cols, uint32_t box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static std::mutex mu;
+    static EncodeFn fn = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!fn) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+            if (e != cudaSuccess) return (int)e;
+            if (q != cudaDriverEntryPointSuccess || !p) return BEVGEN_E_UNSUPPORTED;
+            fn = reinterpret_cast<EncodeFn>(p);
+        }
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)kW, (cuuint64_t)kH, (cuuint64_t)planes};
+    const cuuint64_t gstride[2] = {(cuuint64_t)kW * sizeof(float), (cuuint64_t)kPlane * sizeof(float)};   // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {box_cols, box_rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : BEVGEN_E_INVALID_ARG;
+}
+
 // Timing is a single-caller developer / bench facility: begin/end pairs of one launch are bracketed by the same lock
 // holder only in the sense that the lists stay consistent; concurrent launchers may interleave their records.
 void timing_begin(const char* name, cudaStream_t st) {

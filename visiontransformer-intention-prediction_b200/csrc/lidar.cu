@@ -617,6 +617,11 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
     if (any_plain && have_points)
         BEVGEN_LAUNCH("k_overflow_red", st, k_overflow_red<<<dim3(kOvfCtas, B * S), 256, 0, st>>>(
                           ovf_cnt, ovf, in.sweep_off, reinterpret_cast<uint32_t*>(out), in.aug, S));
+    CUtensorMap out_map;                                     // [B*S*29, 400, 720] view of `out`, 40 x 72 boxes (k_tile_aug's store)
+    if (n_resampled > 0) {
+        const int rc = make_grid_tensor_map(&out_map, out, (uint64_t)B * S * kZ, kATW, kATH);
+        if (rc) return rc;
+    }
     int next_slot = 0;
     for (int cls = 1; cls < 4; ++cls) {
         AugTileFrames fl;
@@ -628,17 +633,17 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
                 case 1:
                     BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, false><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, false><<<grid, kATThreads, AugTileCfg<true, false>::kSmem, st>>>(
-                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
+                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S));
                     break;
                 case 2:
                     BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<false, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<false, true><<<grid, kATThreads, AugTileCfg<false, true>::kSmem, st>>>(
-                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
+                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S));
                     break;
                 default:
                     BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, true><<<grid, kATThreads, AugTileCfg<true, true>::kSmem, st>>>(
-                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out, in.aug, fl, S));
+                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S));
                     break;
             }
             fl.n = 0;

@@ -61,7 +61,11 @@ template <bool ROT, bool SCL> struct AugTileCfg {
     // source footprint / rotated intermediate (= the resize's source region)
     static constexpr int kT0 = kATH == 40 ? (ROT ? (SCL ? 6400 : 5120) : 3840) : (ROT ? (SCL ? 4096 : 3584) : 2080);
     static constexpr int kT1 = (ROT && SCL) ? kDW * kDH : 0;
-    static constexpr int kSmem = (kATElems + kT0 + kT1) * 4 + kT1 * 2;   // O, T0, T1, list of T1's non-zeros (u16)
+    // output tiles: the store of channel z is ONE asynchronous tensor-map copy, so a second tile lets channel z + 1 be built
+    // while it drains; rotate + scale has no room for one (3 CTAs / SM) and does not need it: its O is only written in the
+    // second half of a channel's work
+    static constexpr int kOBufs = (ROT && SCL) ? 1 : 2;
+    static constexpr int kSmem = (kOBufs * kATElems + kT0 + kT1) * 4 + kT1 * 2;   // O (x kOBufs), T0, T1, list of T1's non-zeros (u16)
     static constexpr int kMinBlocks = kATThreads == 256 ? ((ROT && SCL) ? 3 : 4) : ((ROT && SCL) ? 6 : 8);
 };
 
@@ -408,13 +412,14 @@ template <bool ROT, bool SCL>
 __global__ void __launch_bounds__(kATThreads, AugTileCfg<ROT, SCL>::kMinBlocks)
 k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, const uint32_t* __restrict__ ovf_cnt,
            const OvfRec* __restrict__ ovf, const int32_t* __restrict__ sweep_off, const uint32_t* __restrict__ cnt2,
-           const uint2* __restrict__ bins2, float* __restrict__ out, const bevgen_aug_params* __restrict__ params,
-           AugTileFrames fl, int S) {
+           const uint2* __restrict__ bins2, const __grid_constant__ CUtensorMap out_map,
+           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S) {
     static_assert(ROT || SCL, "frames that neither rotate nor scale go through k_tile_store");
     using Cfg = AugTileCfg<ROT, SCL>;
     extern __shared__ __align__(128) unsigned char at_smem[];
-    float* const O = reinterpret_cast<float*>(at_smem);
-    float* const T0 = O + kATElems;
+    float* const O0 = reinterpret_cast<float*>(at_smem);
+    float* const T0 = O0 + Cfg::kOBufs * kATElems;
+    static_assert((kATElems * 4) % 128 == 0, "every output tile buffer must be 128-byte aligned (TMA source)");
     float* const T1 = T0 + Cfg::kT0;
     uint16_t* const W2 = reinterpret_cast<uint16_t*>(T1 + Cfg::kT1);   // indices of T1's non-zeros (ROT && SCL)
     __shared__ bevgen_aug_params P;
@@ -493,7 +498,8 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         if (tid < G.DW) { T.A[tid] = rot_adelta(P.minv, G.dx0 + tid); T.B[tid] = rot_bdelta(P.minv, G.dx0 + tid); }
         else if (tid >= 80 && tid - 80 < G.DH) { T.X0[tid - 80] = rot_X0(P.minv, G.dy0 + tid - 80); T.Y0[tid - 80] = rot_Y0(P.minv, G.dy0 + tid - 80); }
     }
-    for (int i = tid; i < (kATElems + Cfg::kT0 + Cfg::kT1) / 4; i += kATThreads) reinterpret_cast<float4*>(at_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < (Cfg::kOBufs * kATElems + Cfg::kT0 + Cfg::kT1) / 4; i += kATThreads) reinterpret_cast<float4*>(at_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) prefetch_tensormap(&out_map);
     __syncthreads();
     if (SCL && !ROT && tid < G.QH && T.yl[tid] - T.yf[tid] >= kATRows) __trap();   // (scale factors >= 1.45; the host refuses them)
     const int FW = G.FW, FH = G.FH, fx0 = G.fx0, fy0 = G.fy0;
@@ -507,14 +513,21 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         cp_async_commit();                                   // (an empty group keeps the wait_group arithmetic uniform)
         binp += (size_t)kATTiles * kATCap;
     };
-    float* oplane = out + ((size_t)(fdst * S + sweep) * kZ) * kPlane + (size_t)oy0 * kW + ox0;
+    const int plane0 = (fdst * S + sweep) * kZ;                 // plane index of channel 0 in the [planes, 400, 720] view
+    auto zero_tile = [&](float* Ot) {
+        for (int i = tid; i < kATElems / 4; i += kATThreads) reinterpret_cast<float4*>(Ot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
 
 #ifdef BEVGEN_AT_PROFILE
     constexpr int PROF_TID = BEVGEN_AT_PROFILE;
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
 #pragma unroll 1
-    for (int z = 0; z < kZ; ++z, oplane += kPlane) {
+    for (int z = 0; z < kZ; ++z) {
+        float* const O = O0 + (Cfg::kOBufs == 2 ? (z & 1) * kATElems : 0);
+        // the tile this channel builds was last stored two channels ago (kOBufs == 2; thread 0 waited for that copy's smem
+        // reads before the last barrier) -- clear it now, B starts after the next barrier
+        if (Cfg::kOBufs == 2 && z >= 2) zero_tile(O);
         const uint32_t n = cN[z];
         const bool slow = n > (uint32_t)kATCap;              // uniform: over-full bin (dense scene)
         const uint32_t nw = slow ? 0u : n;
@@ -528,7 +541,9 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         }
         if (slow && FW > 0) at_slow_fill(&SA, z, fx0, fy0, FW, FH, T0);
         AT_TICK(1);
+        if (Cfg::kOBufs == 1 && z > 0 && tid == 0) bulk_wait_read<0>();   // single tile: the previous channel's copy has read it
         __syncthreads();
+        if (Cfg::kOBufs == 1 && z > 0) zero_tile(O);            // (not written before the barrier in front of the resize stage)
         AT_TICK(2);
         load_records(z + 2);                                  // (Rs[z & 1] is free: every thread has read its slot)
         AT_TICK(3);
@@ -576,14 +591,15 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
             }
         }
         AT_TICK(4);
+        fence_proxy_async_smem();                            // this thread's writes to O, before the async-proxy read below
         __syncthreads();
         AT_TICK(5);
-        // ---- C: O -> HBM (each thread re-zeroes the float4s it has just read), clear the touched entries of T0 / T1 ------
-        for (int i = tid; i < kATElems / 4; i += kATThreads) {
-            const int r = i / (kATW / 4);
-            const float4 val = reinterpret_cast<const float4*>(O)[i];
-            reinterpret_cast<float4*>(O)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __stcs(reinterpret_cast<float4*>(oplane + r * kW) + (i - r * (kATW / 4)), val);
+        // ---- C: O -> HBM as ONE tensor-map bulk copy (40 x 72 box of plane z), asynchronous: the next channel is built
+        //      while it drains; clear the touched entries of T0 / T1 ----------------------------------------------------
+        if (tid == 0) {
+            tensor_store_3d(&out_map, ox0, oy0, plane0 + z, O);
+            bulk_commit();
+            if (Cfg::kOBufs == 2) bulk_wait_read<1>();       // the copy of channel z - 1 has read its tile: free for z + 1
         }
         if (!slow) {
             if ((uint32_t)tid < nw) { const uint32_t w = W[tid]; T0[at_pos_y(w) * FW + at_pos_x(w)] = 0.f; }
@@ -598,6 +614,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         __syncthreads();
         AT_TICK(7);
     }
+    if (tid == 0) bulk_wait_read<0>();                        // shared memory must outlive the last copies' reads
 #ifdef BEVGEN_AT_PROFILE
     if (tid == PROF_TID) { for (int k = 0; k < 8; ++k) atomicAdd(&g_at_prof[k], (unsigned long long)prof[k]); atomicAdd(&g_at_prof[8], 1ull); }
 #endif
