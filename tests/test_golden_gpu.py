@@ -80,3 +80,12 @@ def test_fused_generation_plus_augmentation_golden(bg):
     got = bg.augment.lidar_bev_augmented(pts, torch.from_numpy(off).to(dev), tf, B, S, params, max_sweep_points=mx).cpu().numpy()
     for b, sd in enumerate(seeds):
         assert np.array_equal(got[b], dense(z, f"s{sd}")), (sd, params[b])
+
+
+@pytest.mark.parametrize("algo", [0, 1, 2])
+def test_lidar_av2_columns_golden(bg, algo):
+    """AV2 column entry point (7 B/point) vs the reference's own grid for feather-stored sweeps (dataset.py:311-347)"""
+    z = load("lidar_av2_columns.npz")
+    pc = bg.PointColumns.from_arrays(z["x"], z["y"], z["z"], z["intensity"])
+    got = bg.lidar_bev_from_sweeps(pc, z["sweep_offsets"], z["rel_tf"], 1, 10, algo=algo)[0].cpu().numpy()
+    assert np.array_equal(got, dense(z, "bev"))
