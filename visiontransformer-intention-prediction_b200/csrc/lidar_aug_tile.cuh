@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kATThreads, AugTileCfg<ROT, SCL>::kMinBlocks)
 k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, const uint32_t* __restrict__ ovf_cnt,
            const OvfRec* __restrict__ ovf, const int32_t* __restrict__ sweep_off, const uint32_t* __restrict__ cnt2,
            const uint2* __restrict__ bins2, const __grid_constant__ CUtensorMap out_map,
-           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S) {
+           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S, int l2_hints) {
     static_assert(ROT || SCL, "frames that neither rotate nor scale go through k_tile_store");
     using Cfg = AugTileCfg<ROT, SCL>;
     extern __shared__ __align__(128) unsigned char at_smem[];
@@ -597,7 +597,8 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         // ---- C: O -> HBM as ONE tensor-map bulk copy (40 x 72 box of plane z), asynchronous: the next channel is built
         //      while it drains; clear the touched entries of T0 / T1 ----------------------------------------------------
         if (tid == 0) {
-            tensor_store_3d(&out_map, ox0, oy0, plane0 + z, O);
+            if (l2_hints) tensor_store_3d_hint(&out_map, ox0, oy0, plane0 + z, O, l2_policy_evict_first());   // records stay in L2
+            else tensor_store_3d(&out_map, ox0, oy0, plane0 + z, O);
             bulk_commit();
             if (Cfg::kOBufs == 2) bulk_wait_read<1>();       // the copy of channel z - 1 has read its tile: free for z + 1
         }
