@@ -49,7 +49,7 @@ def test_host_offsets_are_validated(bg):
 @pytest.mark.parametrize("algo", [0, 1])
 def test_malformed_device_offsets_are_clamped(bg, co, algo):
     """device-resident offsets cannot be checked on the host without a sync: ranges are clamped to the point array and
-    disordered ranges are empty -- no out-of-bounds access (compute-sanitizer clean), well-formed sweeps unaffected."""
+    disordered ranges are empty, so no row outside the point array is ever addressed; well-formed sweeps are unaffected."""
     f = bg.synthetic.frame_c2(6, n=2_000)
     dev = torch.device("cuda", torch.cuda.current_device())
     off = f.sweep_offsets.astype(np.int32).copy()
