@@ -116,16 +116,26 @@ def main():
             forward(r0["lidar_bev"], r0["map_bev"])
 
     def generator_only(n):
+        # the host stays at most two steps ahead of the GPU (as bench.py's e2e loop does): the staging tensors of a finished
+        # step go back to the allocator instead of forcing a fresh cudaMalloc per step
         h = pf.submit(batch)
+        done = []
         for i in range(n):
+            if len(done) >= 2:
+                done.pop(0).synchronize()
             cur, h = h, (pf.submit(batch) if i + 1 < n else None)
             pf.run(cur, aug, out_lidar=bufs[i % 2][0], out_map=bufs[i % 2][1])
+            ev = torch.cuda.Event()
+            ev.record()
+            done.append(ev)
 
     def fed(n):
         # generation of batch i+1 on gen_stream while the forward of batch i runs on fwd_stream; two output buffers
         done_fwd = [None, None]
         h = pf.submit(batch)
         for i in range(n):
+            if done_fwd[i % 2] is not None:
+                done_fwd[i % 2].synchronize()                     # host at most two steps ahead (bounded staging memory)
             with torch.cuda.stream(gen_stream):
                 if done_fwd[i % 2] is not None:
                     gen_stream.wait_event(done_fwd[i % 2])            # the buffer's previous consumer has finished
