@@ -166,3 +166,17 @@ def test_sweep_cache_is_byte_bounded():
     assert len(c) == 0 and c.nbytes == 0
     c.put("a", blk())
     assert len(c) == 0
+
+
+def test_map_cache_is_entry_bounded(bg, tmp_path):
+    from bevgen_b200.maps import LruDict
+    d = LruDict(2)
+    d.store("a", 1); d.store("b", 2)
+    assert d.lookup("a") == 1                    # a is now the most recent
+    d.store("c", 3)
+    assert list(d) == ["a", "c"] and d.lookup("b") is None
+    md = bg.synthetic.synthetic_map(seed=1, rows=2, cols=2, n_cross=1)
+    p = bg.synthetic.write_map_json(md, tmp_path / "m.json")
+    bg.maps.clear_cache()
+    a = bg.maps.load_map_json(p)
+    assert bg.maps.load_map_json(p) is a and bg.maps.load_map_json(p, use_cache=False) is not a

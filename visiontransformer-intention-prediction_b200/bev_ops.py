@@ -104,10 +104,14 @@ class PointColumns:
         if any(c.shape[0] != n for c in cols):
             raise ValueError("x, y, z, intensity must have the same length")
         stride = cls.stride_for(n)
-        buf = torch.zeros(7 * stride, dtype=torch.uint8)
-        if pinned and torch.cuda.is_available():
-            buf = buf.pin_memory()
+        # written in place: one pass over the data (pinned blocks come from torch's caching host allocator, so repeated
+        # packs of similar size reuse them); only the padding rows need clearing
+        buf = torch.empty(7 * stride, dtype=torch.uint8, pin_memory=bool(pinned and torch.cuda.is_available()))
         host = buf.numpy()
+        if stride > n:
+            for k in range(3):
+                host[2 * (k * stride + n):2 * (k + 1) * stride] = 0
+            host[6 * stride + n:7 * stride] = 0
         for k, c in enumerate(cols[:3]):
             h = c if c.dtype == np.float16 else c.astype(np.float16)
             if h is not c and not np.array_equal(h.astype(np.float64), c.astype(np.float64), equal_nan=True):

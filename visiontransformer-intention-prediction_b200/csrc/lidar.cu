@@ -212,19 +212,25 @@ constexpr int kTilesPerSweep = kFillPerSweep;                        // 1160
 constexpr int kTileElems = kFillRows * kW;                           // 7200 floats per tile
 struct OvfRec { unsigned long long idx; uint32_t bits; uint32_t pad; };
 
-// CTA-aggregated: a CTA takes kAggChunk consecutive points of one sweep, ranks its records per tile with SHARED
+// CTA-aggregated: a CTA takes AggCfg<ITEMS>::kChunk consecutive points of one sweep, ranks its records per tile with SHARED
 // atomics, then claims each touched tile's slots with ONE global atomic (instead of one per record) and writes
-// the records out.  Shared memory: records (64 KB) + ranks (16 KB) + per-tile count/base (9 KB).
+// the records out.  Shared memory (8 192-point CTAs): records (64 KB) + ranks (16 KB) + per-tile count/base (9 KB).
 constexpr int kAggThreads = 512;
-constexpr int kAggItems = 16;
-constexpr int kAggChunk = kAggThreads * kAggItems;                   // 8192 points per CTA
-constexpr int kAggSmem = kAggChunk * 8 + kAggChunk * 2 + 2 * kTilesPerSweep * 4;   // 91 200 B
+// Points per thread: 16 (8 192 points per CTA, 91 KB of shared memory) for large launches -- fewest global slot claims
+// per record -- and 8 (4 096 points, 50 KB) for small ones, where twice as many half-size CTAs fill the GPU (a single frame
+// is 130 big CTAs on 296 slots; measured B200, us per frame big -> small at batch 1 / 2 / 4: see bin_items_for()).
+constexpr int kAggItemsBig = 16, kAggItemsSmall = 8;
+template <int ITEMS> struct AggCfg {
+    static constexpr int kChunk = kAggThreads * ITEMS;
+    static constexpr int kSmem = kChunk * 8 + kChunk * 2 + 2 * kTilesPerSweep * 4;   // records, ranks, per-tile count / base
+};
 
-template <int MODE>
+template <int MODE, int ITEMS>
 __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32_t* __restrict__ cnt, uint2* __restrict__ bins,
                                                            uint32_t* __restrict__ ovf_cnt, OvfRec* __restrict__ ovf, int bs0, int l2_hints) {
     extern __shared__ __align__(16) unsigned char agg_smem[];
     uint2* const recs = reinterpret_cast<uint2*>(agg_smem);                                   // (bin << 13 | cell, bits)
+    constexpr int kAggItems = ITEMS, kAggChunk = AggCfg<ITEMS>::kChunk;
     uint16_t* const rank = reinterpret_cast<uint16_t*>(agg_smem + kAggChunk * 8);
     uint32_t* const hist = reinterpret_cast<uint32_t*>(agg_smem + kAggChunk * 10);
     uint32_t* const base = hist + kTilesPerSweep;
@@ -501,6 +507,28 @@ __global__ void __launch_bounds__(256) k_transform_points(const T* __restrict__ 
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// k_bin_fixed launch: big CTAs unless they would not even fill two waves of the GPU's 2 x 148 CTA slots
+template <int MODE>
+int launch_bin(const LidarIn& in, int n_sweeps, int max_sweep_points, uint32_t* cnt, uint2* bins, uint32_t* ovf_cnt, OvfRec* ovf,
+               int hints, cudaStream_t st) {
+    const int pad = MODE == 3 ? 7 : 0;           // column vectors are 8-row aligned: a sweep's first chunk may start up to 7 rows early
+    const long long big_ctas = (long long)((max_sweep_points + pad + AggCfg<kAggItemsBig>::kChunk - 1) / AggCfg<kAggItemsBig>::kChunk) * n_sweeps;
+    static const int forced = [] { const char* e = getenv("BEVGEN_BIN_ITEMS"); return e ? atoi(e) : 0; }();   // measurements only
+    const bool small = forced ? forced == kAggItemsSmall : big_ctas < 4 * 148;
+    if (small) {
+        using C = AggCfg<kAggItemsSmall>;
+        BEVGEN_DYN_SMEM((k_bin_fixed<MODE, kAggItemsSmall>), C::kSmem);
+        const dim3 grid((max_sweep_points + pad + C::kChunk - 1) / C::kChunk, n_sweeps);
+        BEVGEN_LAUNCH("k_bin_fixed", st, (k_bin_fixed<MODE, kAggItemsSmall><<<grid, kAggThreads, C::kSmem, st>>>(in, cnt, bins, ovf_cnt, ovf, 0, hints)));
+    } else {
+        using C = AggCfg<kAggItemsBig>;
+        BEVGEN_DYN_SMEM((k_bin_fixed<MODE, kAggItemsBig>), C::kSmem);
+        const dim3 grid((max_sweep_points + pad + C::kChunk - 1) / C::kChunk, n_sweeps);
+        BEVGEN_LAUNCH("k_bin_fixed", st, (k_bin_fixed<MODE, kAggItemsBig><<<grid, kAggThreads, C::kSmem, st>>>(in, cnt, bins, ovf_cnt, ovf, 0, hints)));
+    }
+    return 0;
+}
+
 // L2 residency hints for the tiled path: the record bins are written evict_last and the output tiles evict_first, so that
 // k_tile_store finds its records in L2 instead of reading HBM in the middle of its own write stream.  Pays only while the
 // bins of the whole launch fit in L2 next to the stream -- measured on B200, k_tile_store us/frame without -> with hints:
@@ -574,12 +602,11 @@ int launch_lidar(LidarIn in, int B, int S, long long total_points, int max_sweep
         uint2* bins = reinterpret_cast<uint2*>(wp + L.bins);
         OvfRec* ovf = reinterpret_cast<OvfRec*>(wp + L.ovf);
         BEVGEN_CUDA(cudaMemsetAsync(cnt, 0, (ntiles + (size_t)B * S + 64) * 4, st));
-        BEVGEN_DYN_SMEM(k_bin_fixed<MODE>, kAggSmem);
         // (Measured: splitting the batch into frame groups, with or without overlapping the binning of group g+1 with
         //  the stores of group g on a second stream, is slower than these three whole-batch launches.)
         if (chunks > 0) {
-            const dim3 agg_grid((max_sweep_points + pad + kAggChunk - 1) / kAggChunk, B * S);
-            BEVGEN_LAUNCH("k_bin_fixed", st, k_bin_fixed<MODE><<<agg_grid, kAggThreads, kAggSmem, st>>>(in, cnt, bins, ovf_cnt, ovf, 0, hints));
+            const int rc = launch_bin<MODE>(in, B * S, max_sweep_points, cnt, bins, ovf_cnt, ovf, hints, st);
+            if (rc) return rc;
         }
         BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<(unsigned)ntiles, 128, kFillBytes, st>>>(cnt, bins, out, 0u, hints));
         if (chunks > 0)
@@ -621,14 +648,13 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
     uint32_t* cnt2 = reinterpret_cast<uint32_t*>(wp + L.cnt2);
     uint2* bins2 = reinterpret_cast<uint2*>(wp + L.bins2);
     BEVGEN_CUDA(cudaMemsetAsync(cnt, 0, (ntiles + (size_t)B * S + 64) * 4, st));
-    BEVGEN_DYN_SMEM(k_bin_fixed<MODE>, kAggSmem);
     BEVGEN_DYN_SMEM((k_tile_aug<true, false>), (AugTileCfg<true, false>::kSmem));
     BEVGEN_DYN_SMEM((k_tile_aug<false, true>), (AugTileCfg<false, true>::kSmem));
     BEVGEN_DYN_SMEM((k_tile_aug<true, true>), (AugTileCfg<true, true>::kSmem));
     const bool have_points = max_sweep_points > 0;
     if (have_points) {
-        const dim3 agg_grid((max_sweep_points + (MODE == 3 ? 7 : 0) + kAggChunk - 1) / kAggChunk, B * S);
-        BEVGEN_LAUNCH("k_bin_fixed", st, k_bin_fixed<MODE><<<agg_grid, kAggThreads, kAggSmem, st>>>(in, cnt, bins, ovf_cnt, ovf, 0, hints));
+        const int rc = launch_bin<MODE>(in, B * S, max_sweep_points, cnt, bins, ovf_cnt, ovf, hints, st);
+        if (rc) return rc;
     }
     auto cls_of = [&](int b) { return (params_host[b].do_rotate != 0 ? 1 : 0) | (params_host[b].do_scale != 0 ? 2 : 0); };
     // runs of frames that are not resampled: plain tile stores

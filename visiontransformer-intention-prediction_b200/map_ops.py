@@ -9,7 +9,7 @@
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
@@ -129,16 +129,17 @@ def rasterize_maps_augmented(table: MapTable, map_ids, ego_T, params, *, out: Op
     return out
 
 
-_TABLES: Dict[str, MapTable] = {}
+_TABLES = maps.LruDict(maps.MAX_CACHED_MAPS)     # (path, device) -> one-map device table
 
 
 def table_for_path(map_json_path: str) -> MapTable:
-    """One-map device table per JSON path, parsed and uploaded once (the reference re-parses per sample)."""
-    key = str(map_json_path)
-    t = _TABLES.get(key)
+    """One-map device table per (JSON path, current device), parsed and uploaded once (the reference re-parses per
+    sample); least-recently-used tables beyond ``maps.MAX_CACHED_MAPS`` are dropped."""
+    key = (str(map_json_path), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    t = _TABLES.lookup(key)
     if t is None:
-        t = MapTable([maps.load_map_json(key)])
-        _TABLES[key] = t
+        t = MapTable([maps.load_map_json(key[0])])
+        _TABLES.store(key, t)
     return t
 
 

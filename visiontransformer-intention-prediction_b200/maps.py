@@ -16,9 +16,10 @@ and cached per path, so per frame only the 3x3 ego matrix changes.
 """
 from __future__ import annotations
 
+import collections
 import dataclasses
 import json
-from typing import Dict, List
+from typing import List
 
 import numpy as np
 
@@ -93,20 +94,43 @@ def parse_map_dict(map_data: dict) -> FlatMap:
     return fm
 
 
-_CACHE: Dict[str, FlatMap] = {}
+class LruDict(collections.OrderedDict):
+    """Small entry-bounded LRU (one map per AV2 log: a few hundred KB each; a training run touches ~850 logs)."""
+
+    def __init__(self, max_entries: int) -> None:
+        super().__init__()
+        self.max_entries = int(max_entries)
+
+    def lookup(self, key):
+        if key in self:
+            self.move_to_end(key)
+            return self[key]
+        return None
+
+    def store(self, key, value) -> None:
+        self[key] = value
+        self.move_to_end(key)
+        while len(self) > self.max_entries:
+            self.popitem(last=False)
+
+
+MAX_CACHED_MAPS = 256
+_CACHE = LruDict(MAX_CACHED_MAPS)
 
 
 def load_map_json(path: str, use_cache: bool = True) -> FlatMap:
     """Parse (once) the map JSON at ``path``.  I/O and JSON errors propagate to the caller,
     which maps them to the reference's 'all-zero map + warning' convention (utils.py:111-116)."""
     key = str(path)
-    if use_cache and key in _CACHE:
-        return _CACHE[key]
+    if use_cache:
+        hit = _CACHE.lookup(key)
+        if hit is not None:
+            return hit
     with open(key, "r") as fh:
         data = json.load(fh)
     fm = parse_map_dict(data)
     if use_cache:
-        _CACHE[key] = fm
+        _CACHE.store(key, fm)
     return fm
 
 
