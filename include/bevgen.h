@@ -129,6 +129,20 @@ int bevgen_lidar_bev_fused_cols(const void *x_f16, const void *y_f16, const void
                                 float *out, void *workspace, size_t workspace_bytes, int algo,
                                 bevgen_stream_t stream);
 
+/* Sweep STORE form of the column entry point.  The four column arrays are a device-resident store of `store_rows` rows
+ * holding many sweeps (e.g. every sweep of the logs in use: 0.7 MB per 100 k-point sweep, a whole AV2 split fits in a B200's
+ * HBM); a launch names the sweep of slot k = b*S + s by its first row, sweep_start[k], and sweep_offsets[k+1] - sweep_offsets[k]
+ * is its length (sweep_offsets is the exclusive prefix sum of the lengths, total_points = its last entry).  Frames may
+ * share sweeps -- the reference's samples are 10-sweep sliding windows (dataset.py:174-211), so consecutive samples share 9
+ * of their 10 sweeps -- and a step then uploads only the sweeps that are not resident yet instead of every frame's 10.
+ * Same arithmetic and bits as bevgen_lidar_bev_fused_cols. */
+int bevgen_lidar_bev_store_cols(const void *x_f16, const void *y_f16, const void *z_f16, const uint8_t *intensity_u8,
+                                int64_t store_rows, const int32_t *sweep_start, const int32_t *sweep_offsets,
+                                const double *rel_tf, int B, int S, int64_t total_points, int max_sweep_points,
+                                const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,
+                                float *out, void *workspace, size_t workspace_bytes, int algo,
+                                bevgen_stream_t stream);
+
 int bevgen_lidar_bev_ego_f64(const double *pts3, const float *intensity, const int32_t *sweep_offsets,
                              int B, int S, int64_t total_points, int max_sweep_points,
                              const uint8_t *flip, const int32_t *drop_rects, const int32_t *drop_counts,
@@ -212,6 +226,13 @@ int bevgen_lidar_bev_augmented_cols(const void *x_f16, const void *y_f16, const 
                                     int B, int S, int64_t total_points, int max_sweep_points,
                                     const bevgen_aug_params *params, const bevgen_aug_params *params_host,
                                     float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
+
+/* bevgen_lidar_bev_augmented on a sweep store (see bevgen_lidar_bev_store_cols) */
+int bevgen_lidar_bev_store_augmented_cols(const void *x_f16, const void *y_f16, const void *z_f16, const uint8_t *intensity_u8,
+                                          int64_t store_rows, const int32_t *sweep_start, const int32_t *sweep_offsets,
+                                          const double *rel_tf, int B, int S, int64_t total_points, int max_sweep_points,
+                                          const bevgen_aug_params *params, const bevgen_aug_params *params_host,
+                                          float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
 
 /* rasterize_map_ego_centric followed by the image part of augment_bev (utils.py:508-511) on the 9 map channels, per-frame
  * parameters as in bevgen_augment (device copy + host copy): frames that neither rotate nor scale get flip / dropout

@@ -160,7 +160,8 @@ def fused_supported(params: Sequence[AugParams], packed: Optional[np.ndarray] = 
 
 def lidar_bev_augmented(points4: torch.Tensor, sweep_offsets: torch.Tensor, rel_tf: torch.Tensor, num_frames: int,
                         num_sweeps: int, params: Sequence[AugParams], *, max_sweep_points: int,
-                        out: Optional[torch.Tensor] = None, packed: Optional[np.ndarray] = None) -> torch.Tensor:
+                        out: Optional[torch.Tensor] = None, packed: Optional[np.ndarray] = None, sweep_start=None,
+                        total_points: Optional[int] = None) -> torch.Tensor:
     """create_intentnet_lidar_bev (utils.py:62-106) + the image part of augment_bev (utils.py:508-511) for a batch, every
     output byte written once: frames that rotate / scale are built directly in augmented form from the binned point
     records (csrc/lidar_aug_tile.cuh) instead of generate -> read back -> resample -> write.  Device tensors in
@@ -190,9 +191,19 @@ def lidar_bev_augmented(points4: torch.Tensor, sweep_offsets: torch.Tensor, rel_
         dparams = _dev(hparams, torch.uint8, device)
         L = _native.lib()
         n = pts.n if cols else int(pts.shape[0])
+        start = None
+        if sweep_start is not None:            # sweep store form (bev_ops.lidar_bev_from_sweeps)
+            if not cols or total_points is None:
+                raise ValueError("sweep_start needs PointColumns and total_points")
+            start = _dev(sweep_start, torch.int32, device)
+            store_rows, n = n, int(total_points)
         wbytes = int(L.bevgen_lidar_aug_workspace_bytes(n, B, S, sum(1 for p in params if p.needs_gather)))
         ws = workspace.get("lidar", wbytes, device)
-        if cols:
+        if start is not None:
+            rc = L.bevgen_lidar_bev_store_augmented_cols(*pts.ptrs(), store_rows, _ptr(start), _ptr(off), _ptr(tf), B, S, n,
+                                                         int(max_sweep_points), _ptr(dparams), C.c_void_p(hparams.ctypes.data),
+                                                         _ptr(out), _ptr(ws), wbytes, _stream_ptr())
+        elif cols:
             rc = L.bevgen_lidar_bev_augmented_cols(*pts.ptrs(), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
                                                    _ptr(dparams), C.c_void_p(hparams.ctypes.data), _ptr(out), _ptr(ws), wbytes,
                                                    _stream_ptr())

@@ -261,16 +261,21 @@ def _aug_fusion_args(B, flip, drop_rects, drop_counts, device):
 # =========================================================================== batched fast path
 def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_sweeps: int = LIDAR_SWEEPS, *,
                           max_sweep_points: Optional[int] = None, flip=None, drop_rects=None, drop_counts=None,
-                          out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED) -> torch.Tensor:
+                          out: Optional[torch.Tensor] = None, algo: int = ALGO_TILED, sweep_start=None,
+                          total_points: Optional[int] = None) -> torch.Tensor:
     """Fused dataset.py:339-340 + utils.py:62-106 for ``num_frames`` frames.
 
     points4        float32 (16 B/pt) or float16 (8 B/pt) [N,4]  (x, y, z, intensity) in each sweep's own frame, sweeps
                    concatenated -- or a ``PointColumns`` (AV2's on-disk columns: float16 x,y,z + uint8 intensity, 7 B/pt)
     sweep_offsets  int32 [B*S+1]  CSR offsets; an empty range = missing sweep (its 29 channels stay 0)
     rel_tf         float64 [B*S,4,4]  ego_SE3_world @ sweep_SE3 (pose.sweep_rel_transforms)
+    sweep_start    sweep STORE form (PointColumns only): int32 [B*S] first row of every sweep in a resident store; the sweeps'
+                   lengths are then ``diff(sweep_offsets)`` and ``total_points`` their sum (sweep_store.SweepStore)
     returns        float32 CUDA tensor [B, S*29, 400, 720]
     """
     cols = points4 if isinstance(points4, PointColumns) else None
+    if sweep_start is not None and cols is None:
+        raise ValueError("sweep_start (sweep store form) needs the points as PointColumns")
     device = _device_of(cols.buf if cols is not None else points4, sweep_offsets, rel_tf, out)
     B, S = int(num_frames), int(num_sweeps)
     host_off = None
@@ -292,6 +297,13 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
             n = int(pts.shape[0])
         if off.numel() != B * S + 1 or tf.shape[0] != B * S:
             raise ValueError("sweep_offsets must have B*S+1 entries and rel_tf B*S matrices")
+        store_rows = n
+        start = None
+        if sweep_start is not None:
+            start = _dev(sweep_start, torch.int32, device)
+            if start.numel() != B * S or total_points is None:
+                raise ValueError("sweep_start must have B*S entries and total_points (sum of the sweep lengths) must be given")
+            n = int(total_points)              # the offsets are a prefix sum of lengths here: they add up to n, not to the store
         if host_off is not None:
             max_sweep_points = _check_offsets(host_off, n, max_sweep_points)
         elif max_sweep_points is None:
@@ -308,7 +320,11 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
         if algo == ALGO_TILED:
             wbytes = int(L.bevgen_lidar_workspace_bytes(n, B, S))
             ws = workspace.get("lidar", wbytes, device)
-        if cols is not None:
+        if start is not None:
+            rc = L.bevgen_lidar_bev_store_cols(*pts.ptrs(), store_rows, _ptr(start), _ptr(off), _ptr(tf), B, S, n,
+                                               int(max_sweep_points), _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes,
+                                               int(algo), _stream_ptr())
+        elif cols is not None:
             rc = L.bevgen_lidar_bev_fused_cols(*pts.ptrs(), _ptr(off), _ptr(tf), B, S, n, int(max_sweep_points),
                                                _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
         else:

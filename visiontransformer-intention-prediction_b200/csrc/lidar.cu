@@ -42,7 +42,11 @@ struct LidarIn {
     const double* rel_tf;      // MODE 0: [B*S,16]
     const double* pts3;        // MODE 1
     const float* intensity;    // MODE 1
-    const int32_t* sweep_off;  // [B*S+1]
+    const int32_t* sweep_off;  // [B*S+1] CSR offsets: sweep k owns rows [sweep_off[k], sweep_off[k+1]) -- and, always, the
+                               // slice [sweep_off[k] - sweep_off[0], ...) of the overflow list
+    const int32_t* sweep_start = nullptr;   // [B*S] or null.  Sweep STORE form: sweep k owns rows [sweep_start[k], sweep_start[k] +
+                               // sweep_off[k+1] - sweep_off[k]) of a resident point store, so frames may share sweeps (sliding
+                               // windows) and sweeps need not be contiguous; sweep_off is then only the prefix sum of lengths
     const uint8_t* flip;       // [B] or null
     const int32_t* rects;      // [B,5,4] or null
     const int32_t* nrects;     // [B] or null
@@ -56,11 +60,12 @@ struct LidarIn {
 // Row range of sweep `bs`, made safe against malformed CSR offsets (they live in device memory, the host cannot check them
 // without a synchronisation): clamped to the point array, empty when it is not ordered after the first offset.
 __device__ __forceinline__ void sweep_range(const LidarIn& in, int bs, int& beg, int& end) {
-    const int off0 = in.sweep_off[0];
-    beg = in.sweep_off[bs]; end = in.sweep_off[bs + 1];
-    beg = beg < 0 ? 0 : beg;
-    end = end > in.n_points ? in.n_points : end;
-    if (beg < off0 || off0 < 0) end = beg;
+    const int lb0 = in.sweep_off[0], lb = in.sweep_off[bs];
+    int len = in.sweep_off[bs + 1] - lb;
+    if (lb0 < 0 || lb < lb0 || len < 0) len = 0;       // (also keeps the sweep's overflow-list slice inside the list)
+    beg = in.sweep_start ? in.sweep_start[bs] : lb;
+    if (beg < 0 || beg > in.n_points) { beg = 0; len = 0; }
+    end = beg + (len < in.n_points - beg ? len : in.n_points - beg);
 }
 
 inline LidarIn make_in(const uint2* h4, const float4* p4, const double* rel_tf, const double* p3, const float* inten,
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
     // per-sweep lists: sweep bs owns ovf[sweep_off[bs] - sweep_off[0] ...) (a point spills at most once), count in ovf_cnt[bs]
     if (tid == 0) s_spill_base = atomicAdd(ovf_cnt + bs, s_spill_n);
     __syncthreads();
-    const uint32_t obase = (uint32_t)(beg - in.sweep_off[0]) + s_spill_base;
+    const uint32_t obase = (uint32_t)(in.sweep_off[bs] - in.sweep_off[0]) + s_spill_base;
 #pragma unroll 1
     for (int it = 0; it < kAggItems; ++it) {
         const int k = it * kAggThreads + tid;
@@ -560,12 +565,16 @@ TiledWorkspace tiled_layout(long long total_points, int B, int S, int n_resample
     return w;
 }
 
+// total_points = rows the sweeps of this launch add up to (sizes the overflow lists); store_rows = rows of the point array
+// the ranges are clamped to (-1: the same -- CSR form, where the sweeps tile the array)
 template <int MODE>
 int launch_lidar(LidarIn in, int B, int S, long long total_points, int max_sweep_points, float* out,
-                 void* workspace, size_t workspace_bytes, int algo, cudaStream_t st) {
-    if (B <= 0 || S <= 0 || total_points < 0 || total_points > 0x7FFFFFFFll || max_sweep_points < 0 || !out || !in.sweep_off)
+                 void* workspace, size_t workspace_bytes, int algo, cudaStream_t st, long long store_rows = -1) {
+    if (store_rows < 0) store_rows = total_points;
+    if (B <= 0 || S <= 0 || total_points < 0 || total_points > 0x7FFFFFFFll || store_rows > 0x7FFFFFFFll || max_sweep_points < 0 ||
+        !out || !in.sweep_off)
         return BEVGEN_E_INVALID_ARG;
-    in.n_points = (int)total_points;
+    in.n_points = (int)store_rows;
     if ((in.rects == nullptr) != (in.nrects == nullptr)) return BEVGEN_E_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;      // TMA bulk stores need 16 B alignment
     const size_t ntiles = (size_t)B * S * kTilesPerSweep;
@@ -624,11 +633,12 @@ int launch_lidar(LidarIn in, int B, int S, long long total_points, int max_sweep
 template <int MODE>
 int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int max_sweep_points,
                            const bevgen_aug_params* params_host, float* out, void* workspace, size_t workspace_bytes,
-                           cudaStream_t st) {
-    if (B <= 0 || S <= 0 || total_points < 0 || total_points > 0x7FFFFFFFll || max_sweep_points < 0 || !out || !in.sweep_off ||
-        !in.aug || !params_host)
+                           cudaStream_t st, long long store_rows = -1) {
+    if (store_rows < 0) store_rows = total_points;
+    if (B <= 0 || S <= 0 || total_points < 0 || total_points > 0x7FFFFFFFll || store_rows > 0x7FFFFFFFll || max_sweep_points < 0 ||
+        !out || !in.sweep_off || !in.aug || !params_host)
         return BEVGEN_E_INVALID_ARG;
-    in.n_points = (int)total_points;
+    in.n_points = (int)store_rows;
     if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BEVGEN_E_INVALID_ARG;
     const size_t ntiles = (size_t)B * S * kTilesPerSweep;
     if (ntiles > 0x7FFFFFFFull || (unsigned)(B * S) > 65535u || B > 32767) return BEVGEN_E_UNSUPPORTED;
@@ -821,6 +831,34 @@ extern "C" int bevgen_lidar_bev_augmented_cols(const void* x_f16, const void* y_
     return launch_lidar_augmented<3>(make_cols(x_f16, y_f16, z_f16, intensity_u8, rel_tf, sweep_offsets, nullptr, nullptr, nullptr, S, params),
                                      B, S, total_points, max_sweep_points, params_host, out, workspace, workspace_bytes,
                                      static_cast<cudaStream_t>(stream));
+}
+
+// ---- sweep STORE form: the column arrays are a resident store of many sweeps; a frame names its sweeps by start row -------
+extern "C" int bevgen_lidar_bev_store_cols(const void* x_f16, const void* y_f16, const void* z_f16, const uint8_t* intensity_u8,
+                                           int64_t store_rows, const int32_t* sweep_start, const int32_t* sweep_offsets,
+                                           const double* rel_tf, int B, int S, int64_t total_points, int max_sweep_points,
+                                           const uint8_t* flip, const int32_t* drop_rects, const int32_t* drop_counts, float* out,
+                                           void* workspace, size_t workspace_bytes, int algo, bevgen_stream_t stream) {
+    if (store_rows < 0 || !sweep_start || (total_points > 0 && !rel_tf)) return BEVGEN_E_INVALID_ARG;
+    if (!cols_ok(x_f16, y_f16, z_f16, intensity_u8, store_rows)) return BEVGEN_E_INVALID_ARG;
+    LidarIn in = make_cols(x_f16, y_f16, z_f16, intensity_u8, rel_tf, sweep_offsets, flip, drop_rects, drop_counts, S, nullptr);
+    in.sweep_start = sweep_start;
+    return launch_lidar<3>(in, B, S, total_points, max_sweep_points, out, workspace, workspace_bytes, algo,
+                           static_cast<cudaStream_t>(stream), store_rows);
+}
+
+extern "C" int bevgen_lidar_bev_store_augmented_cols(const void* x_f16, const void* y_f16, const void* z_f16,
+                                                     const uint8_t* intensity_u8, int64_t store_rows, const int32_t* sweep_start,
+                                                     const int32_t* sweep_offsets, const double* rel_tf, int B, int S,
+                                                     int64_t total_points, int max_sweep_points, const bevgen_aug_params* params,
+                                                     const bevgen_aug_params* params_host, float* out, void* workspace,
+                                                     size_t workspace_bytes, bevgen_stream_t stream) {
+    if (store_rows < 0 || !sweep_start || (total_points > 0 && !rel_tf)) return BEVGEN_E_INVALID_ARG;
+    if (!cols_ok(x_f16, y_f16, z_f16, intensity_u8, store_rows)) return BEVGEN_E_INVALID_ARG;
+    LidarIn in = make_cols(x_f16, y_f16, z_f16, intensity_u8, rel_tf, sweep_offsets, nullptr, nullptr, nullptr, S, params);
+    in.sweep_start = sweep_start;
+    return launch_lidar_augmented<3>(in, B, S, total_points, max_sweep_points, params_host, out, workspace, workspace_bytes,
+                                     static_cast<cudaStream_t>(stream), store_rows);
 }
 
 extern "C" int bevgen_lidar_bev_ego_f64(const double* pts3, const float* intensity, const int32_t* sweep_offsets, int B, int S,

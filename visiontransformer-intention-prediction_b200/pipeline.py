@@ -146,11 +146,22 @@ class BevGenerator:
             self._scratch[key] = t
         return t
 
-    def upload(self, batch: FrameBatch) -> dict:
-        """Async H2D of the packed batch (pinned -> device) on the current stream."""
+    def upload(self, batch) -> dict:
+        """Async H2D of the packed batch (pinned -> device) on the current stream.  A ``sweep_store.StoreBatch`` uploads only
+        its per-frame tables: the points are the store's resident columns (the stream waits for the store's uploads)."""
         d = self.device
-        return {"points4": batch.points4.to(d, non_blocking=True), "sweep_offsets": batch.sweep_offsets.to(d, non_blocking=True),
-                "rel_tf": batch.rel_tf.to(d, non_blocking=True), "ego_T": batch.ego_T.to(d, non_blocking=True)}
+        dv = {"sweep_offsets": batch.sweep_offsets.to(d, non_blocking=True),
+              "rel_tf": batch.rel_tf.to(d, non_blocking=True), "ego_T": batch.ego_T.to(d, non_blocking=True)}
+        store = getattr(batch, "store", None)
+        if store is not None:
+            if store.device != d:
+                raise ValueError(f"sweep store lives on {store.device}, generator on {d}")
+            dv["points4"] = store.columns
+            dv["sweep_start"] = batch.sweep_start.to(d, non_blocking=True)
+            store.ready(torch.cuda.current_stream(d))
+        else:
+            dv["points4"] = batch.points4.to(d, non_blocking=True)
+        return dv
 
     def generate(self, batch: FrameBatch, aug: Optional[Sequence[_aug.AugParams]] = None, *, dev: Optional[dict] = None,
                  with_map: bool = True, out_lidar: Optional[torch.Tensor] = None,
@@ -196,6 +207,12 @@ class BevGenerator:
         d_T = dv["ego_T"]
         ids = batch.map_ids
 
+        store = getattr(batch, "store", None)
+        if store is not None and dev is not None:
+            store.ready(torch.cuda.current_stream(self.device))
+        d_start = dv.get("sweep_start")          # sweep store form: first store row per sweep
+        skw = {} if d_start is None else {"total_points": batch.total_points}
+
         def run(lo: int, hi: int, dst_l: torch.Tensor, dst_m: Optional[torch.Tensor]) -> None:
             """generate frames [lo, hi) into dst_l / dst_m (sub-ranges are pointer offsets: CSR offsets are absolute)"""
             sl = slice(lo, hi)
@@ -203,7 +220,8 @@ class BevGenerator:
                                           hi - lo, S, max_sweep_points=batch.max_sweep_points,
                                           flip=None if d_flip is None else d_flip[sl],
                                           drop_rects=None if d_rects is None else d_rects[sl],
-                                          drop_counts=None if d_cnt is None else d_cnt[sl], out=dst_l, algo=self.algo)
+                                          drop_counts=None if d_cnt is None else d_cnt[sl], out=dst_l, algo=self.algo,
+                                          sweep_start=None if d_start is None else d_start[lo * S:hi * S], **skw)
             if with_map:
                 with torch.cuda.stream(self._map_stream):
                     map_ops.rasterize_maps(self.map_table, ids[sl], d_T[sl], flip=None if d_flip is None else d_flip[sl],
@@ -216,7 +234,8 @@ class BevGenerator:
         if packed is not None:
             # LiDAR: one pass for the whole batch, whatever the frame order (no partition needed)
             _aug.lidar_bev_augmented(dv["points4"], dv["sweep_offsets"], dv["rel_tf"], B, S, aug,
-                                     max_sweep_points=batch.max_sweep_points, out=out_lidar, packed=packed)
+                                     max_sweep_points=batch.max_sweep_points, out=out_lidar, packed=packed,
+                                     sweep_start=d_start, **skw)
             if with_map:
                 # map channels: resampled straight from the rasterizer's bit planes, on the side stream
                 with torch.cuda.stream(self._map_stream):
@@ -237,6 +256,8 @@ class BevGenerator:
                 _aug.augment_grid(gen_m, gp, out=out_map[:J])
         if with_map:
             main.wait_stream(self._map_stream)
+        if store is not None:
+            store.consumed(main)                 # rows read by this call may be overwritten by uploads ordered after this point
         lid, mp = out_lidar, (out_map if with_map else None)
         return {"lidar_bev": lid, "map_bev": mp}
 
@@ -266,6 +287,8 @@ class PrefetchingGenerator:
         batch, dev, ev = handle
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
+        store = getattr(batch, "store", None)
         for t in dev.values():
-            t.record_stream(cur)          # allocated on the copy stream, consumed on the compute stream
+            if store is None or t is not store.columns:
+                t.record_stream(cur)      # allocated on the copy stream, consumed on the compute stream
         return self.gen.generate(batch, aug, dev=dev, **kw)

@@ -1,0 +1,191 @@
+"""Device-resident sweep store: upload every sweep ONCE, name it in as many frames as use it.
+
+The reference's samples are 10-sweep sliding windows over a log (dataset.py:174-211), so consecutive samples share 9 of
+their 10 sweeps -- and its Dataset re-reads and re-transforms all 10 for every sample (dataset.py:305-342).  The per-sweep
+pose transform depends on the sample's own ego pose and cannot be shared, but the raw points can: in AV2's column form a
+100 k-point sweep is 0.7 MB, a log of ~150 sweeps ~100 MB, and a whole split fits in a B200's 180 GB of HBM.  With a store a
+step moves only the sweeps that are not resident yet over PCIe (one per new sample in a sliding-window stream) instead of
+ten per frame; the kernels are the same ones, reading their sweeps through a start row per sweep
+(``bevgen_lidar_bev_store_cols``), and the grids are bit-identical.
+
+    store = SweepStore(capacity_points=64_000_000)
+    store.put(("log7", ts), x, y, z, intensity)                  # float16 x 3 + uint8, as the feather file holds them
+    batch = StoreBatch.pack(store, [StoreFrame(keys, sweep_poses, current_pose), ...])
+    out = BevGenerator(...).generate(batch)                       # same call as for a FrameBatch
+"""
+from __future__ import annotations
+
+import collections
+import dataclasses
+from typing import Hashable, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import bev_ops, pose
+from .constants import LIDAR_SWEEPS
+
+
+def _round8(n: int) -> int:
+    return (int(n) + 7) // 8 * 8
+
+
+class SweepStore:
+    """Ring of sweeps in one device ``PointColumns`` buffer; first-in-first-out eviction when it wraps.
+
+    Uploads run on the store's own copy stream and overlap the kernels of earlier steps; ``ready(stream)`` makes a compute
+    stream wait for them, ``consumed(stream)`` marks the point after which rows may be overwritten (an upload that evicts
+    waits for it).  Capacity must cover the sweeps of the batches in flight -- a batch whose sweep was evicted before it
+    was launched fails in ``StoreBatch.pack`` (KeyError), it is never silently wrong."""
+
+    def __init__(self, capacity_points: int, device: Optional[torch.device] = None) -> None:
+        self.device = torch.device(device) if device is not None else bev_ops._require_cuda()
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.capacity = max(8, _round8(capacity_points))
+        with torch.cuda.device(self.device):
+            buf = torch.zeros(7 * self.capacity, dtype=torch.uint8, device=self.device)
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.columns = bev_ops.PointColumns(buf, self.capacity, self.capacity)       # every row readable: n = capacity
+        self._entries: "collections.OrderedDict[Hashable, Tuple[int, int]]" = collections.OrderedDict()   # ring order
+        self._head = 0
+        self._uploaded: Optional[torch.cuda.Event] = None
+        self._consumed: Optional[torch.cuda.Event] = None
+        self.h2d_bytes = 0                      # bytes uploaded since construction (bench accounting)
+        self.evictions = 0
+
+    def __contains__(self, key: Hashable) -> bool:
+        return key in self._entries
+
+    def __len__(self) -> int:
+        return len(self._entries)
+
+    def rows(self, key: Hashable) -> Tuple[int, int]:
+        """(first row, number of points) of a resident sweep; KeyError when it is not (never uploaded, or evicted)."""
+        return self._entries[key]
+
+    def _alloc(self, need: int) -> Tuple[int, bool]:
+        if need > self.capacity:
+            raise ValueError(f"sweep of {need} rows does not fit a store of {self.capacity}")
+        evicted = False
+        if self._head + need > self.capacity:                       # wrap: the rows up to the end go first ...
+            while self._entries and next(iter(self._entries.values()))[0] >= self._head:
+                self._entries.popitem(last=False); evicted = True; self.evictions += 1
+            self._head = 0
+        lo, hi = self._head, self._head + need                      # ... then whatever lies under the new rows
+        while self._entries:
+            r, n = next(iter(self._entries.values()))
+            if r < hi and lo < r + max(8, _round8(n)):
+                self._entries.popitem(last=False); evicted = True; self.evictions += 1
+            else:
+                break
+        self._head = hi
+        return lo, evicted
+
+    def put(self, key: Hashable, x, y, z, intensity) -> Tuple[int, int]:
+        """Make sweep ``key`` resident (no-op when it is): ``x, y, z`` float16 and ``intensity`` uint8 arrays / tensors of one
+        length, as AV2 stores them; pinned sources are copied asynchronously.  Returns (first row, points)."""
+        hit = self._entries.get(key)
+        if hit is not None:
+            return hit
+        cols = []
+        for c, dt in zip((x, y, z, intensity), (torch.float16, torch.float16, torch.float16, torch.uint8)):
+            t = c if isinstance(c, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(c))
+            if t.dtype != dt:
+                raise ValueError("SweepStore.put takes AV2's stored dtypes: float16 x, y, z and uint8 intensity "
+                                 "(PointColumns.from_arrays converts losslessly or raises)")
+            cols.append(t.reshape(-1))
+        n = int(cols[0].numel())
+        if any(int(t.numel()) != n for t in cols):
+            raise ValueError("x, y, z, intensity must have the same length")
+        row, evicted = self._alloc(max(8, _round8(n)))
+        cap, buf = self.capacity, self.columns.buf
+        with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
+            if evicted and self._consumed is not None:
+                self.copy_stream.wait_event(self._consumed)          # kernels that may still read the overwritten rows
+            for k, t in enumerate(cols[:3]):
+                buf[2 * (k * cap + row):2 * (k * cap + row + n)].view(torch.float16).copy_(t, non_blocking=True)
+            buf[6 * cap + row:6 * cap + row + n].copy_(cols[3], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._uploaded = ev
+        self._entries[key] = (row, n)
+        self.h2d_bytes += 7 * n
+        return row, n
+
+    def ready(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """``stream`` (default: current) waits for every upload issued so far."""
+        if self._uploaded is not None:
+            (stream or torch.cuda.current_stream(self.device)).wait_event(self._uploaded)
+
+    def consumed(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Call after enqueuing kernels that read the store: later evicting uploads wait for this point of ``stream``."""
+        ev = torch.cuda.Event()
+        ev.record(stream or torch.cuda.current_stream(self.device))
+        self._consumed = ev
+
+
+@dataclasses.dataclass
+class StoreFrame:
+    """One sample of a sliding-window stream: the keys of its sweeps (oldest first; ``None`` = missing sweep, its 29 channels
+    stay zero like the reference's ``None`` entries, utils.py:75-76) and the poses dataset.py:285-339 looks up for them."""
+    keys: Sequence[Optional[Hashable]]
+    sweep_poses: np.ndarray          # float64 [S,7] tx,ty,tz,qx,qy,qz,qw
+    current_pose: np.ndarray         # float64 [7]
+    gt: Optional[dict] = None
+
+
+@dataclasses.dataclass
+class StoreBatch:
+    """What ``BevGenerator.generate`` needs for a batch of StoreFrames: a few hundred bytes per frame, pinned."""
+    store: SweepStore
+    sweep_start: torch.Tensor        # int32 [B*S]   first store row of every sweep (0 for missing ones)
+    sweep_offsets: torch.Tensor      # int32 [B*S+1] exclusive prefix sum of the sweep lengths
+    rel_tf: torch.Tensor             # float64 [B*S,16]
+    ego_T: torch.Tensor              # float64 [B,9]
+    map_ids: np.ndarray
+    num_frames: int
+    num_sweeps: int
+    max_sweep_points: int
+    total_points: int
+
+    points_format = "av2-store"
+    point_bytes = 7
+
+    @property
+    def num_points(self) -> int:
+        return self.total_points
+
+    @property
+    def h2d_bytes(self) -> int:
+        """per-call bytes (the sweeps themselves are accounted by ``SweepStore.h2d_bytes`` when they are uploaded)"""
+        return int(self.sweep_start.numel() * 4 + self.sweep_offsets.numel() * 4 + self.rel_tf.numel() * 8 + self.ego_T.numel() * 8)
+
+    @staticmethod
+    def pack(store: SweepStore, frames: Sequence[StoreFrame], num_sweeps: int = LIDAR_SWEEPS,
+             map_ids: Optional[Sequence[int]] = None) -> "StoreBatch":
+        B, S = len(frames), int(num_sweeps)
+        start = np.zeros((B, S), np.int32)
+        counts = np.zeros((B, S), np.int64)
+        rel = np.tile(np.eye(4), (B, S, 1, 1))
+        ego = np.tile(np.eye(3), (B, 1, 1))
+        for b, f in enumerate(frames):
+            ns = len(f.keys)
+            if ns > S:
+                raise IndexError(f"frame {b}: {ns} sweeps but num_sweeps={S}")      # utils.py:102
+            for s, key in enumerate(f.keys):
+                if key is None:
+                    continue
+                start[b, s], counts[b, s] = store.rows(key)                         # KeyError: not resident (any more)
+            rel[b, :ns] = pose.sweep_rel_transforms(f.current_pose, f.sweep_poses)  # dataset.py:285-339
+            cp = np.asarray(f.current_pose, np.float64)
+            ego[b] = pose.map_matrix_from_pose(cp[0], cp[1], cp[3:7])               # utils.py:121-129
+        off = np.zeros(B * S + 1, np.int64)
+        off[1:] = np.cumsum(counts.reshape(-1))
+        if off[-1] >= 2 ** 31:
+            raise ValueError("more than 2^31 points in one batch")
+        pin = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if torch.cuda.is_available() else \
+              (lambda a: torch.from_numpy(np.ascontiguousarray(a)))
+        ids = np.full(B, -1, np.int64) if map_ids is None else np.asarray(map_ids, np.int64)
+        return StoreBatch(store, pin(start.reshape(-1)), pin(off.astype(np.int32)), pin(rel.reshape(B * S, 16)), pin(ego.reshape(B, 9)),
+                          ids, B, S, int(counts.max()) if B else 0, int(off[-1]))

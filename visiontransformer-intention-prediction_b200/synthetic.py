@@ -103,6 +103,33 @@ def frame_c4(frame_idx: int = 0, n: int = 100_000, S: int = LIDAR_SWEEPS) -> Fra
     return _finish(sweeps, _poses(S))
 
 
+def sliding_log(num_sweeps: int, n: int = 100_000, seed: int = 0, dense: bool = False):
+    """A synthetic LOG: ``num_sweeps`` consecutive sweeps (config-2 point distribution, or config-4 clusters with
+    ``dense``; coordinates already rounded to float16 values, as AV2 stores them) with a moving ego, from which the
+    reference's Dataset would cut 10-sweep sliding windows (dataset.py:174-211).  Returns (sweeps, poses): a list of
+    float32 ``[n,4]`` arrays and float64 ``[num_sweeps,7]``."""
+    rng = np.random.default_rng(1000 * 6 + seed)
+    centres = np.array([[10.0, -5.0], [25.0, 12.0], [-4.0, 30.0], [40.0, -40.0]])
+    sweeps = []
+    for _ in range(num_sweeps):
+        p = np.empty((n, 4), np.float32)
+        if dense:
+            c = centres[rng.integers(0, 4, n)]
+            p[:, 0] = c[:, 0] + rng.normal(0, 0.3, n); p[:, 1] = c[:, 1] + rng.normal(0, 0.3, n); p[:, 2] = rng.uniform(-1, 1, n)
+        else:
+            p[:, 0] = rng.normal(0, 35, n); p[:, 1] = rng.normal(0, 35, n); p[:, 2] = rng.uniform(-3, 5, n)
+        p[:, 3] = rng.integers(0, 256, n)
+        p[:, :3] = p[:, :3].astype(np.float16).astype(np.float32)
+        sweeps.append(p)
+    return sweeps, _poses(num_sweeps)
+
+
+def window_frame(sweeps, poses: np.ndarray, first: int, S: int = LIDAR_SWEEPS, map_data=None) -> Frame:
+    """The sample whose sweeps are ``first .. first + S - 1`` of a log (current pose = the newest sweep's, as in
+    dataset.py:285-301 where the sample's timestamp is its last sweep's)."""
+    return _finish([sweeps[first + k] for k in range(S)], poses[first:first + S].copy(), map_data)
+
+
 def quantize_f16(frame: Frame) -> Frame:
     """Round the point coordinates to float16-representable values (what AV2 sweeps hold on disk: float16 x,y,z and
     uint8 intensity), in place.  Such frames can be packed at 8 B/point (FrameBatch.pack(points_dtype=np.float16))."""
