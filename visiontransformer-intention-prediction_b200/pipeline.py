@@ -257,7 +257,7 @@ class BevGenerator:
         if with_map:
             main.wait_stream(self._map_stream)
         if store is not None:
-            store.consumed(main)                 # rows read by this call may be overwritten by uploads ordered after this point
+            store.consumed(main, batch)          # rows read by this call may be overwritten by uploads ordered after this point
         lid, mp = out_lidar, (out_map if with_map else None)
         return {"lidar_bev": lid, "map_bev": mp}
 

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import collections
 import dataclasses
+import weakref
 from typing import Hashable, Optional, Sequence, Tuple
 
 import numpy as np
@@ -34,9 +35,12 @@ class SweepStore:
     """Ring of sweeps in one device ``PointColumns`` buffer; first-in-first-out eviction when it wraps.
 
     Uploads run on the store's own copy stream and overlap the kernels of earlier steps; ``ready(stream)`` makes a compute
-    stream wait for them, ``consumed(stream)`` marks the point after which rows may be overwritten (an upload that evicts
-    waits for it).  Capacity must cover the sweeps of the batches in flight -- a batch whose sweep was evicted before it
-    was launched fails in ``StoreBatch.pack`` (KeyError), it is never silently wrong."""
+    stream wait for them.  ``StoreBatch.pack`` pins the sweeps it names; ``consumed(stream, batch)`` (made by
+    ``BevGenerator.generate``) closes an epoch, unpins them and stamps them with it.  An upload that overwrites a sweep's
+    rows first waits for the event of the sweep's last epoch -- not for the newest kernels, so uploads for step i+1 still
+    overlap the kernels of step i.  Capacity must cover the sweeps of the batches in flight: a batch whose sweep is gone
+    fails in ``StoreBatch.pack`` (KeyError), and an upload that would overwrite a pinned sweep raises -- never silently
+    wrong."""
 
     def __init__(self, capacity_points: int, device: Optional[torch.device] = None) -> None:
         self.device = torch.device(device) if device is not None else bev_ops._require_cuda()
@@ -46,11 +50,16 @@ class SweepStore:
         with torch.cuda.device(self.device):
             buf = torch.zeros(7 * self.capacity, dtype=torch.uint8, device=self.device)
             self.copy_stream = torch.cuda.Stream(device=self.device)
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))     # uploads are ordered after the clear
         self.columns = bev_ops.PointColumns(buf, self.capacity, self.capacity)       # every row readable: n = capacity
         self._entries: "collections.OrderedDict[Hashable, Tuple[int, int]]" = collections.OrderedDict()   # ring order
         self._head = 0
         self._uploaded: Optional[torch.cuda.Event] = None
-        self._consumed: Optional[torch.cuda.Event] = None
+        self._epoch = 0                         # number of consumed() calls so far
+        self._events = {}                       # epoch -> event recorded by consumed()
+        self._last_use = {}                     # key -> epoch of the last consumed batch that named it
+        self._pins = collections.Counter()      # key -> packed batches that name it and have not been consumed yet
+        self._wait_epoch = 0                    # set by _alloc: newest epoch an evicted sweep was used in
         self.h2d_bytes = 0                      # bytes uploaded since construction (bench accounting)
         self.evictions = 0
 
@@ -64,23 +73,41 @@ class SweepStore:
         """(first row, number of points) of a resident sweep; KeyError when it is not (never uploaded, or evicted)."""
         return self._entries[key]
 
-    def _alloc(self, need: int) -> Tuple[int, bool]:
+    def _pin(self, keys) -> None:
+        self._pins.update(keys)
+
+    def _unpin(self, keys) -> None:
+        self._pins.subtract(keys)
+        for k in keys:
+            if self._pins[k] <= 0:
+                del self._pins[k]
+
+    def _evict_front(self) -> None:
+        key = next(iter(self._entries))
+        if self._pins.get(key, 0) > 0:
+            raise RuntimeError("SweepStore too small: this upload would overwrite a sweep that a packed batch which has not been "
+                               "generated yet still names")
+        self._entries.popitem(last=False)
+        self._wait_epoch = max(self._wait_epoch, self._last_use.pop(key, 0))
+        self.evictions += 1
+
+    def _alloc(self, need: int) -> int:
         if need > self.capacity:
             raise ValueError(f"sweep of {need} rows does not fit a store of {self.capacity}")
-        evicted = False
+        self._wait_epoch = 0
         if self._head + need > self.capacity:                       # wrap: the rows up to the end go first ...
             while self._entries and next(iter(self._entries.values()))[0] >= self._head:
-                self._entries.popitem(last=False); evicted = True; self.evictions += 1
+                self._evict_front()
             self._head = 0
         lo, hi = self._head, self._head + need                      # ... then whatever lies under the new rows
         while self._entries:
             r, n = next(iter(self._entries.values()))
             if r < hi and lo < r + max(8, _round8(n)):
-                self._entries.popitem(last=False); evicted = True; self.evictions += 1
+                self._evict_front()
             else:
                 break
         self._head = hi
-        return lo, evicted
+        return lo
 
     def put(self, key: Hashable, x, y, z, intensity) -> Tuple[int, int]:
         """Make sweep ``key`` resident (no-op when it is): ``x, y, z`` float16 and ``intensity`` uint8 arrays / tensors of one
@@ -98,11 +125,12 @@ class SweepStore:
         n = int(cols[0].numel())
         if any(int(t.numel()) != n for t in cols):
             raise ValueError("x, y, z, intensity must have the same length")
-        row, evicted = self._alloc(max(8, _round8(n)))
+        row = self._alloc(max(8, _round8(n)))
         cap, buf = self.capacity, self.columns.buf
         with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
-            if evicted and self._consumed is not None:
-                self.copy_stream.wait_event(self._consumed)          # kernels that may still read the overwritten rows
+            ev_used = self._events.get(self._wait_epoch)
+            if ev_used is not None:
+                self.copy_stream.wait_event(ev_used)                 # the last kernels that read the rows being overwritten
             for k, t in enumerate(cols[:3]):
                 buf[2 * (k * cap + row):2 * (k * cap + row + n)].view(torch.float16).copy_(t, non_blocking=True)
             buf[6 * cap + row:6 * cap + row + n].copy_(cols[3], non_blocking=True)
@@ -118,11 +146,21 @@ class SweepStore:
         if self._uploaded is not None:
             (stream or torch.cuda.current_stream(self.device)).wait_event(self._uploaded)
 
-    def consumed(self, stream: Optional[torch.cuda.Stream] = None) -> None:
-        """Call after enqueuing kernels that read the store: later evicting uploads wait for this point of ``stream``."""
+    def consumed(self, stream: Optional[torch.cuda.Stream] = None, batch: Optional["StoreBatch"] = None) -> None:
+        """Call after enqueuing the kernels that read ``batch``'s sweeps: uploads that later overwrite those sweeps wait for
+        this point of ``stream``."""
         ev = torch.cuda.Event()
         ev.record(stream or torch.cuda.current_stream(self.device))
-        self._consumed = ev
+        self._epoch += 1
+        self._events[self._epoch] = ev
+        if batch is not None:
+            for k in batch.keys:
+                if k in self._entries:
+                    self._last_use[k] = self._epoch
+            batch._release()
+        if len(self._events) > 64:              # older epochs: their kernels finished long before any row comes round again
+            for k in sorted(self._events)[:-64]:
+                del self._events[k]
 
 
 @dataclasses.dataclass
@@ -133,6 +171,8 @@ class StoreFrame:
     sweep_poses: np.ndarray          # float64 [S,7] tx,ty,tz,qx,qy,qz,qw
     current_pose: np.ndarray         # float64 [7]
     gt: Optional[dict] = None
+    rel_tf: Optional[np.ndarray] = None      # [len(keys),4,4] if the caller has done the pose prep already (pose.sweep_rel_transforms)
+    ego_T: Optional[np.ndarray] = None       # [3,3]                                                       (pose.map_matrix_from_pose)
 
 
 @dataclasses.dataclass
@@ -148,6 +188,8 @@ class StoreBatch:
     num_sweeps: int
     max_sweep_points: int
     total_points: int
+    keys: tuple = ()                 # distinct sweeps named (pinned in the store until the batch is generated or dropped)
+    _finalizer: object = None
 
     points_format = "av2-store"
     point_bytes = 7
@@ -160,6 +202,11 @@ class StoreBatch:
     def h2d_bytes(self) -> int:
         """per-call bytes (the sweeps themselves are accounted by ``SweepStore.h2d_bytes`` when they are uploaded)"""
         return int(self.sweep_start.numel() * 4 + self.sweep_offsets.numel() * 4 + self.rel_tf.numel() * 8 + self.ego_T.numel() * 8)
+
+    def _release(self) -> None:
+        """unpin the batch's sweeps (idempotent; also runs when the batch is garbage-collected without being generated)"""
+        if self._finalizer is not None and self._finalizer.alive:
+            self._finalizer()
 
     @staticmethod
     def pack(store: SweepStore, frames: Sequence[StoreFrame], num_sweeps: int = LIDAR_SWEEPS,
@@ -177,9 +224,15 @@ class StoreBatch:
                 if key is None:
                     continue
                 start[b, s], counts[b, s] = store.rows(key)                         # KeyError: not resident (any more)
-            rel[b, :ns] = pose.sweep_rel_transforms(f.current_pose, f.sweep_poses)  # dataset.py:285-339
-            cp = np.asarray(f.current_pose, np.float64)
-            ego[b] = pose.map_matrix_from_pose(cp[0], cp[1], cp[3:7])               # utils.py:121-129
+            if f.rel_tf is not None:
+                rel[b, :ns] = f.rel_tf
+            else:
+                rel[b, :ns] = pose.sweep_rel_transforms(f.current_pose, f.sweep_poses)  # dataset.py:285-339
+            if f.ego_T is not None:
+                ego[b] = f.ego_T
+            else:
+                cp = np.asarray(f.current_pose, np.float64)
+                ego[b] = pose.map_matrix_from_pose(cp[0], cp[1], cp[3:7])           # utils.py:121-129
         off = np.zeros(B * S + 1, np.int64)
         off[1:] = np.cumsum(counts.reshape(-1))
         if off[-1] >= 2 ** 31:
@@ -187,5 +240,9 @@ class StoreBatch:
         pin = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if torch.cuda.is_available() else \
               (lambda a: torch.from_numpy(np.ascontiguousarray(a)))
         ids = np.full(B, -1, np.int64) if map_ids is None else np.asarray(map_ids, np.int64)
-        return StoreBatch(store, pin(start.reshape(-1)), pin(off.astype(np.int32)), pin(rel.reshape(B * S, 16)), pin(ego.reshape(B, 9)),
-                          ids, B, S, int(counts.max()) if B else 0, int(off[-1]))
+        keys = tuple({k for f in frames for k in f.keys if k is not None})
+        batch = StoreBatch(store, pin(start.reshape(-1)), pin(off.astype(np.int32)), pin(rel.reshape(B * S, 16)), pin(ego.reshape(B, 9)),
+                           ids, B, S, int(counts.max()) if B else 0, int(off[-1]), keys)
+        store._pin(keys)
+        batch._finalizer = weakref.finalize(batch, store._unpin, keys)
+        return batch
