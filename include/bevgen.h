@@ -227,6 +227,12 @@ int bevgen_lidar_bev_augmented_cols(const void *x_f16, const void *y_f16, const 
                                     const bevgen_aug_params *params, const bevgen_aug_params *params_host,
                                     float *out, void *workspace, size_t workspace_bytes, bevgen_stream_t stream);
 
+/* Upload one sweep's columns into a sweep store: dst_* = device addresses of the sweep's first row in the store's x / y / z /
+ * intensity columns, src_* = HOST arrays of n float16 / float16 / float16 / uint8 values (asynchronous on `stream` when they
+ * are pinned).  This is the sweep-decode boundary of dataset.py:311-321: the four Arrow column buffers go over as they are. */
+int bevgen_store_put_cols(void *dst_x, void *dst_y, void *dst_z, void *dst_i, const void *src_x, const void *src_y,
+                          const void *src_z, const void *src_i, int64_t n, bevgen_stream_t stream);
+
 /* bevgen_lidar_bev_augmented on a sweep store (see bevgen_lidar_bev_store_cols) */
 int bevgen_lidar_bev_store_augmented_cols(const void *x_f16, const void *y_f16, const void *z_f16, const uint8_t *intensity_u8,
                                           int64_t store_rows, const int32_t *sweep_start, const int32_t *sweep_offsets,

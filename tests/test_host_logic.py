@@ -180,3 +180,31 @@ def test_map_cache_is_entry_bounded(bg, tmp_path):
     bg.maps.clear_cache()
     a = bg.maps.load_map_json(p)
     assert bg.maps.load_map_json(p) is a and bg.maps.load_map_json(p, use_cache=False) is not a
+
+
+def test_sweep_store_ring_allocation_and_pins():
+    """the store's row allocator (host logic only: no device buffer is touched): first-in-first-out eviction across the wrap,
+    8-row alignment, pinned sweeps are never overwritten"""
+    import collections
+    from bevgen_b200.sweep_store import SweepStore
+    s = SweepStore.__new__(SweepStore)
+    s.capacity, s._entries, s._head, s._epoch, s._events = 64, collections.OrderedDict(), 0, 0, {}
+    s._last_use, s._pins, s._wait_epoch, s.evictions = {}, collections.Counter(), 0, 0
+
+    def put(k, n):
+        r = s._alloc(max(8, (n + 7) // 8 * 8))
+        s._entries[k] = (r, n)
+        return r
+
+    assert [put(0, 20), put(1, 20)] == [0, 24] and s._head == 48
+    assert put(2, 20) == 0 and list(s._entries) == [1, 2]           # wrapped: sweep 0 evicted, sweep 1 (rows 24..47) still there
+    s._last_use[1] = 5
+    assert put(3, 20) == 24 and list(s._entries) == [2, 3] and s._wait_epoch == 5   # evicting 1 -> wait for its last epoch
+    s._pin([2])
+    with pytest.raises(RuntimeError):
+        put(4, 20)                                                   # would overwrite pinned sweep 2
+    assert list(s._entries) == [2, 3]
+    s._unpin([2])
+    assert put(4, 20) == 0 and 2 not in s._entries and not s._pins
+    with pytest.raises(ValueError):
+        s._alloc(72)

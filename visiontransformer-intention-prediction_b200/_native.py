@@ -70,6 +70,7 @@ PROTOTYPES = {
     "bevgen_lidar_bev_fused_f16": (_i, [_p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),
     "bevgen_lidar_bev_fused_cols": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),
     "bevgen_lidar_bev_augmented_cols": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),
+    "bevgen_store_put_cols": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "bevgen_lidar_bev_store_cols": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),
     "bevgen_lidar_bev_store_augmented_cols": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),
     "bevgen_lidar_bev_ego_f64": (_i, [_p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),

@@ -122,6 +122,20 @@ extern "C" int bevgen_timing_collect(char* buf, size_t cap) {
     return (int)n;
 }
 
+// Sweep store upload: the four columns of one sweep, host -> device, asynchronous on `stream` when the sources are pinned.
+extern "C" int bevgen_store_put_cols(void* dst_x, void* dst_y, void* dst_z, void* dst_i, const void* src_x, const void* src_y,
+                                     const void* src_z, const void* src_i, int64_t n, bevgen_stream_t stream) {
+    if (n < 0) return BEVGEN_E_INVALID_ARG;
+    if (n == 0) return 0;
+    if (!dst_x || !dst_y || !dst_z || !dst_i || !src_x || !src_y || !src_z || !src_i) return BEVGEN_E_INVALID_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BEVGEN_CUDA(cudaMemcpyAsync(dst_x, src_x, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+    BEVGEN_CUDA(cudaMemcpyAsync(dst_y, src_y, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+    BEVGEN_CUDA(cudaMemcpyAsync(dst_z, src_z, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+    BEVGEN_CUDA(cudaMemcpyAsync(dst_i, src_i, (size_t)n, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
 extern "C" int bevgen_abi_version(void) { return BEVGEN_ABI_VERSION; }
 
 extern "C" void bevgen_constants(double* out) {

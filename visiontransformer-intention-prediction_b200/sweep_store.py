@@ -23,7 +23,7 @@ from typing import Hashable, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import bev_ops, pose
+from . import _native, bev_ops, pose
 from .constants import LIDAR_SWEEPS
 
 
@@ -55,6 +55,9 @@ class SweepStore:
         self._entries: "collections.OrderedDict[Hashable, Tuple[int, int]]" = collections.OrderedDict()   # ring order
         self._head = 0
         self._uploaded: Optional[torch.cuda.Event] = None
+        self._dirty = False                     # uploads issued since the last event on the copy stream
+        self._pending_sources = []              # host arrays of those uploads (kept alive until their event has completed)
+        self._inflight = collections.deque()
         self._epoch = 0                         # number of consumed() calls so far
         self._events = {}                       # epoch -> event recorded by consumed()
         self._last_use = {}                     # key -> epoch of the last consumed batch that named it
@@ -115,34 +118,52 @@ class SweepStore:
         hit = self._entries.get(key)
         if hit is not None:
             return hit
-        cols = []
-        for c, dt in zip((x, y, z, intensity), (torch.float16, torch.float16, torch.float16, torch.uint8)):
-            t = c if isinstance(c, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(c))
-            if t.dtype != dt:
-                raise ValueError("SweepStore.put takes AV2's stored dtypes: float16 x, y, z and uint8 intensity "
-                                 "(PointColumns.from_arrays converts losslessly or raises)")
-            cols.append(t.reshape(-1))
-        n = int(cols[0].numel())
-        if any(int(t.numel()) != n for t in cols):
-            raise ValueError("x, y, z, intensity must have the same length")
+        ptrs, keep, n = [], [], None
+        for c, dt, npdt in zip((x, y, z, intensity), (torch.float16,) * 3 + (torch.uint8,), (np.float16,) * 3 + (np.uint8,)):
+            if isinstance(c, torch.Tensor):
+                if c.dtype != dt or c.is_cuda or not c.is_contiguous():
+                    c = None
+                else:
+                    ptrs.append(c.data_ptr()); m = int(c.numel())
+            else:
+                c = np.ascontiguousarray(c)
+                if c.dtype != npdt:
+                    c = None
+                else:
+                    ptrs.append(c.ctypes.data); m = int(c.size)
+            if c is None:
+                raise ValueError("SweepStore.put takes contiguous host arrays in AV2's stored dtypes: float16 x, y, z and uint8 "
+                                 "intensity (PointColumns.from_arrays converts losslessly or raises)")
+            keep.append(c)
+            if n is None:
+                n = m
+            elif m != n:
+                raise ValueError("x, y, z, intensity must have the same length")
         row = self._alloc(max(8, _round8(n)))
-        cap, buf = self.capacity, self.columns.buf
-        with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
-            ev_used = self._events.get(self._wait_epoch)
-            if ev_used is not None:
-                self.copy_stream.wait_event(ev_used)                 # the last kernels that read the rows being overwritten
-            for k, t in enumerate(cols[:3]):
-                buf[2 * (k * cap + row):2 * (k * cap + row + n)].view(torch.float16).copy_(t, non_blocking=True)
-            buf[6 * cap + row:6 * cap + row + n].copy_(cols[3], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
-        self._uploaded = ev
+        cap, base = self.capacity, self.columns.buf.data_ptr()
+        ev_used = self._events.get(self._wait_epoch)
+        if ev_used is not None:
+            self.copy_stream.wait_event(ev_used)                     # the last kernels that read the rows being overwritten
+        # one call, four async copies on the store's copy stream (pageable sources are staged by the driver before it returns)
+        rc = _native.lib().bevgen_store_put_cols(base + 2 * row, base + 2 * (cap + row), base + 2 * (2 * cap + row), base + 6 * cap + row,
+                                                 *ptrs, n, self.copy_stream.cuda_stream)
+        _native.check(rc, "bevgen_store_put_cols")
+        self._pending_sources.append(keep)                           # pinned sources must outlive the copy
+        self._dirty = True
         self._entries[key] = (row, n)
         self.h2d_bytes += 7 * n
         return row, n
 
     def ready(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """``stream`` (default: current) waits for every upload issued so far."""
+        if self._dirty:
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+            self._uploaded, self._dirty = ev, False
+            self._inflight.append((ev, self._pending_sources))
+            self._pending_sources = []
+            while self._inflight and self._inflight[0][0].query():   # drop references to sources whose copies have completed
+                self._inflight.popleft()
         if self._uploaded is not None:
             (stream or torch.cuda.current_stream(self.device)).wait_event(self._uploaded)
 
