@@ -124,3 +124,25 @@ def test_ring_eviction_and_wraparound(bg, co):
         store.put("f32", np.zeros(4, np.float32), np.zeros(4, np.float16), np.zeros(4, np.float16), np.zeros(4, np.uint8))
     with pytest.raises(ValueError):
         store.put("too big", *(np.zeros(10**6, np.float16),) * 3, np.zeros(10**6, np.uint8))
+
+
+def test_batch_loader_with_store_equals_loader_without(bg):
+    """BevBatchLoader(sweep_store=...): sliding-window samples that carry sweep_keys share their sweeps through the store;
+    same batches (train-time augmentation included) as packing every sample's own ten sweeps"""
+    S = 10
+    sweeps, poses = bg.synthetic.sliding_log(15, n=3_001, seed=9)
+    samples = []
+    for i in range(5):
+        f = bg.synthetic.window_frame(sweeps, poses, i)
+        f.sweep_keys = [("log", i + k) for k in range(S)]
+        samples.append(f)
+    store = bg.SweepStore(capacity_points=15 * 3_008)
+    for train in (False, True):
+        random.seed(11)
+        a = list(bg.dataset_shim.BevBatchLoader(samples, 2, is_train=train))
+        random.seed(11)
+        b = list(bg.dataset_shim.BevBatchLoader(samples, 2, is_train=train, sweep_store=store))
+        assert len(a) == len(b) == 3
+        for x, y in zip(a, b):
+            assert torch.equal(x["lidar_bev"], y["lidar_bev"])
+    assert len(store) == 14 and store.h2d_bytes == 14 * 3_001 * 7        # 5 windows over 14 distinct sweeps, each sent once

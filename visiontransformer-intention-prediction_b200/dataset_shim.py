@@ -69,13 +69,39 @@ class BevBatchLoader:
 
     def __init__(self, samples: Sequence, batch_size: int, map_table: Optional[map_ops.MapTable] = None,
                  map_id_of: Optional[Callable] = None, is_train: bool = False, num_sweeps: int = 10,
-                 algo: int = bev_ops.ALGO_TILED, drop_last: bool = False, keep_order: bool = True) -> None:
+                 algo: int = bev_ops.ALGO_TILED, drop_last: bool = False, keep_order: bool = True,
+                 sweep_store=None) -> None:
+        """``sweep_store`` (a ``sweep_store.SweepStore``): samples that carry ``sweep_keys`` (one hashable per sweep, e.g.
+        (log id, timestamp)) have each sweep uploaded once and shared by every sample that names it -- the reference's
+        samples are sliding windows that share 9 of their 10 sweeps (dataset.py:174-211)."""
         self.samples, self.bs, self.is_train, self.S = samples, int(batch_size), is_train, num_sweeps
+        self.store = sweep_store
         self.map_id_of = map_id_of or (lambda s: 0)
         self.gen = pipeline.BevGenerator(map_table, algo=algo)
         self.with_map = map_table is not None
         self.drop_last = drop_last
         self.keep_order = keep_order     # False: within a batch, resampled frames come first (gt_list permuted alike)
+
+    def _pack_from_store(self, chunk, ids):
+        from . import sweep_store as ss
+        frames = []
+        for smp in chunk:
+            off = np.asarray(smp.sweep_offsets)
+            cols = getattr(smp, "columns", None)
+            keys = list(smp.sweep_keys)
+            for k, key in enumerate(keys):
+                lo, hi = int(off[k]), int(off[k + 1])
+                if hi <= lo:
+                    keys[k] = None                                   # missing / empty sweep (utils.py:75-76)
+                elif key not in self.store:
+                    if cols is not None:
+                        self.store.put(key, *(c[lo:hi] for c in cols))
+                    else:                                            # row samples: split losslessly (or raise)
+                        pc = bev_ops.PointColumns.from_points4(np.asarray(smp.points4)[lo:hi], pinned=False)
+                        h, st, n = pc.buf.numpy(), pc.stride, pc.n
+                        self.store.put(key, *(h[2 * j * st:2 * j * st + 2 * n].view(np.float16) for j in range(3)), h[6 * st:6 * st + n])
+            frames.append(ss.StoreFrame(keys, np.asarray(smp.sweep_poses), np.asarray(smp.current_pose)))
+        return ss.StoreBatch.pack(self.store, frames, self.S, map_ids=ids)
 
     def __len__(self) -> int:
         n = len(self.samples)
@@ -93,7 +119,10 @@ class BevBatchLoader:
                 if not self.keep_order:      # frames that rotate / scale first: no identity copies (order is returned)
                     chunk, aug, _ = pipeline.partition_for_augmentation(chunk, aug)
             ids = [self.map_id_of(s) for s in chunk] if self.with_map else None
-            fb = pipeline.FrameBatch.pack(chunk, self.S, map_ids=ids)
+            if self.store is not None and all(getattr(s, "sweep_keys", None) is not None for s in chunk):
+                fb = self._pack_from_store(chunk, ids)
+            else:
+                fb = pipeline.FrameBatch.pack(chunk, self.S, map_ids=ids)
             for k, s in enumerate(chunk):
                 gt = getattr(s, "gt", None) or {"boxes_xywha": np.zeros((0, 5), np.float32), "intentions": np.zeros((0,), np.int64)}
                 boxes = np.array(gt["boxes_xywha"], dtype=np.float32, copy=True)
