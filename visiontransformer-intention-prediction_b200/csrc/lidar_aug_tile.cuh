@@ -432,7 +432,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     __shared__ uint32_t cN[kZ + 3];                          // this tile's record count per channel (0 past the last one)
     __shared__ AugSlowArgs SA;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int tile = blockIdx.x, bx = tile % kATBX, by = tile / kATBX, sweep = blockIdx.y;
     const int fsrc = fl.src[blockIdx.z], fdst = fl.dst[blockIdx.z], slot = fl.slot[blockIdx.z];
     const int ox0 = bx * kATW, oy0 = by * kATH;
