@@ -1,0 +1,141 @@
+"""An AV2-format log directory -> device-resident BEV batches: the reference's ``ArgoverseIntentNetDataset`` + ``DataLoader`` +
+``collate_fn`` (dataset.py:27-367) as one iterable, with the hot path on the GPU.
+
+What is mirrored from the reference (so that the SAME directory yields the SAME samples in the SAME order):
+  * which sub-directories count as scenarios: ``sensors/lidar/*.feather``, ``annotations.feather``, a non-empty ``map/`` with a
+    ``log_map_archive_<log id>*.json`` (or any ``log_map_archive_*.json``), ``city_SE3_egovehicle.feather``, files of at least
+    1 KiB (``ScenarioValidator._validate_scenario``, dataset.py:101-134)
+  * samples = 10-sweep sliding windows over the sorted sweep timestamps, current timestamp = the newest sweep's
+    (``_create_sequences``, dataset.py:174-211)
+  * per sample: pose lookup, which sweeps count as missing, ``None`` samples (``__getitem__``, dataset.py:285-345; here
+    ``sweep_io.load_frame``)
+What is NOT here: ground truth (``prepare_gt_for_frame``, utils.py:184-225, stays the reference's host code -- pass
+``gt_of(sequence) -> {"boxes_xywha", "intentions"}``), and everything after the batch (models, loss).
+
+Sweeps are decoded as AV2 stores them (float16 x,y,z + uint8 intensity columns) and uploaded ONCE into a device-resident
+``SweepStore``; every sample that names a sweep reads it there (the windows share 9 of their 10 sweeps).
+"""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+from typing import Callable, Iterator, List, Optional
+
+import numpy as np
+
+from . import dataset_shim, map_ops, maps, sweep_io, sweep_store
+from .constants import LIDAR_SWEEPS
+
+
+def find_scenarios(data_dir, min_file_bytes: int = 1024) -> List[dict]:
+    """dataset.py:40-134: the sub-directories of ``data_dir`` that are complete scenarios, in ``os.scandir`` order."""
+    base = Path(data_dir)
+    out = []
+    if not base.is_dir():
+        return out
+    for entry in os.scandir(base):
+        if not entry.is_dir():
+            continue
+        d = Path(entry.path)
+        log_id = d.name
+        lidar, ann, mp, ego = d / "sensors" / "lidar", d / "annotations.feather", d / "map", d / "city_SE3_egovehicle.feather"
+        ok = True
+        for p in (lidar, ann, mp, ego):
+            if not p.exists() or (p.is_dir() and not any(p.iterdir())) or \
+               (p.is_file() and min_file_bytes > 0 and p.stat().st_size < min_file_bytes):
+                ok = False
+        if not ok or not any(lidar.glob("*.feather")):
+            continue
+        files = list(mp.glob(f"log_map_archive_{log_id}*.json")) or list(mp.glob("log_map_archive_*.json"))
+        if not files:
+            continue
+        out.append({"log_id": log_id, "log_dir": str(d), "map_json_path": str(files[0]), "annotations_path": str(ann)})
+    return out
+
+
+def make_sequences(scenarios: List[dict], num_sweeps: int = LIDAR_SWEEPS) -> List[dict]:
+    """dataset.py:174-211: sliding windows of ``num_sweeps`` consecutive sweep files per log."""
+    seqs = []
+    for sc in scenarios:
+        lidar = Path(sc["log_dir"]) / "sensors" / "lidar"
+        try:
+            ts = sorted(int(p.stem) for p in lidar.glob("*.feather"))
+        except ValueError:
+            continue                                                    # a non-numeric file name skips the log (dataset.py:206-207)
+        for i in range(len(ts) - num_sweeps + 1):
+            seqs.append({**sc, "current_ts_ns": ts[i + num_sweeps - 1], "sweep_ts_list": ts[i:i + num_sweeps]})
+    return seqs
+
+
+class _LazySamples:
+    """Sequence view BevBatchLoader slices: sample i is decoded when its batch is built."""
+
+    def __init__(self, ds: "Av2BevDataset", order: List[int]) -> None:
+        self.ds, self.order = ds, order
+
+    def __len__(self) -> int:
+        return len(self.order)
+
+    def __getitem__(self, sl):
+        idx = self.order[sl]
+        return [self.ds.sample(i) for i in idx] if isinstance(sl, slice) else self.ds.sample(idx)
+
+
+class Av2BevDataset:
+    def __init__(self, data_dir, num_sweeps: int = LIDAR_SWEEPS, is_train: bool = False,
+                 gt_of: Optional[Callable[[dict], dict]] = None, store_points: int = 64_000_000, device=None) -> None:
+        self.num_sweeps, self.is_train, self.gt_of = int(num_sweeps), is_train, gt_of
+        self.scenarios = find_scenarios(data_dir)
+        if not self.scenarios:
+            raise ValueError(f"No valid scenarios found in {data_dir}. Please check the path and data integrity.")   # dataset.py:166
+        self.sequences = make_sequences(self.scenarios, self.num_sweeps)
+        if not self.sequences:
+            raise ValueError(f"Could not create any valid sequences from the provided scenarios in {data_dir}.")     # dataset.py:171
+        self._poses = {}
+        self._map_index = {sc["log_id"]: k for k, sc in enumerate(self.scenarios)}
+        self.map_table = map_ops.MapTable([self._load_map(sc["map_json_path"]) for sc in self.scenarios], device=device)
+        self.store = sweep_store.SweepStore(store_points, device=self.map_table.device)
+
+    @staticmethod
+    def _load_map(path: str) -> maps.FlatMap:
+        try:
+            return maps.load_map_json(path)
+        except Exception as e:  # noqa: BLE001 -- utils.py:114: unreadable map -> all-zero map + message
+            print(f"Error loading map JSON {path}: {e}. Returning empty map.")
+            return maps.parse_map_dict({})
+
+    def __len__(self) -> int:
+        return len(self.sequences)
+
+    def _ego_poses(self, seq: dict):
+        df = self._poses.get(seq["log_id"])
+        if df is None:
+            import pyarrow.feather as feather
+            df = feather.read_feather(Path(seq["log_dir"]) / "city_SE3_egovehicle.feather")    # utils.py:22-25
+            self._poses[seq["log_id"]] = df
+        return df
+
+    def sample(self, idx: int):
+        """dataset.py:262-345 up to the hot path: the sample's sweeps (AV2 columns) and poses, or ``None`` where the reference
+        returns ``None``."""
+        seq = self.sequences[idx]
+        fr = sweep_io.load_frame(seq["log_dir"], seq["sweep_ts_list"], seq["current_ts_ns"], self._ego_poses(seq), layout="columns")
+        if fr is None:
+            return None
+        fr.sweep_keys = [(seq["log_id"], int(ts)) for ts in seq["sweep_ts_list"]]
+        fr.map_index = self._map_index[seq["log_id"]]
+        fr.sequence = seq
+        if self.gt_of is not None:
+            fr.gt = self.gt_of(seq)
+        return fr
+
+    def loader(self, batch_size: int = 8, shuffle: bool = False, rng: Optional[np.random.Generator] = None,
+               drop_last: bool = False) -> Iterator[dict]:
+        """Batches like ``DataLoader(dataset, batch_size, shuffle, collate_fn=collate_fn)`` (train_vit.py:76-79), already on the
+        device: ``{"lidar_bev", "map_bev", "gt_list"}``; ``None`` samples are dropped as collate_fn drops them."""
+        order = list(range(len(self)))
+        if shuffle:
+            (rng or np.random.default_rng()).shuffle(order)
+        return iter(dataset_shim.BevBatchLoader(_LazySamples(self, order), batch_size, self.map_table,
+                                                map_id_of=lambda s: s.map_index, is_train=self.is_train,
+                                                num_sweeps=self.num_sweeps, drop_last=drop_last, sweep_store=self.store))
