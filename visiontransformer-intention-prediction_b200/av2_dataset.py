@@ -130,12 +130,43 @@ class Av2BevDataset:
         return fr
 
     def loader(self, batch_size: int = 8, shuffle: bool = False, rng: Optional[np.random.Generator] = None,
-               drop_last: bool = False) -> Iterator[dict]:
+               drop_last: bool = False, decode_threads: int = 0, decode_ahead: int = 2) -> Iterator[dict]:
         """Batches like ``DataLoader(dataset, batch_size, shuffle, collate_fn=collate_fn)`` (train_vit.py:76-79), already on the
-        device: ``{"lidar_bev", "map_bev", "gt_list"}``; ``None`` samples are dropped as collate_fn drops them."""
+        device: ``{"lidar_bev", "map_bev", "gt_list"}``; ``None`` samples are dropped as collate_fn drops them.
+
+        ``decode_threads`` > 0: the sweep files of the next ``decode_ahead`` batches are decoded (feather -> column arrays,
+        into sweep_io's LRU) by a thread pool while the current batch is built and generated -- pyarrow releases the GIL, and
+        after the kernels the decode is what bounds a from-disk loader.  Uploads and launches stay on the calling thread."""
         order = list(range(len(self)))
         if shuffle:
             (rng or np.random.default_rng()).shuffle(order)
-        return iter(dataset_shim.BevBatchLoader(_LazySamples(self, order), batch_size, self.map_table,
-                                                map_id_of=lambda s: s.map_index, is_train=self.is_train,
-                                                num_sweeps=self.num_sweeps, drop_last=drop_last, sweep_store=self.store))
+        inner = dataset_shim.BevBatchLoader(_LazySamples(self, order), batch_size, self.map_table,
+                                            map_id_of=lambda s: s.map_index, is_train=self.is_train,
+                                            num_sweeps=self.num_sweeps, drop_last=drop_last, sweep_store=self.store)
+        if decode_threads <= 0:
+            return iter(inner)
+        return self._prefetching(inner, order, batch_size, decode_threads, decode_ahead)
+
+    def _prefetching(self, inner, order, batch_size, threads, ahead):
+        from concurrent.futures import ThreadPoolExecutor
+        asked = set()
+
+        def request(pool, b):                                           # decode the not-yet-resident sweeps of batch b
+            for i in order[b * batch_size:(b + 1) * batch_size]:
+                seq = self.sequences[i]
+                for ts in seq["sweep_ts_list"]:
+                    key = (seq["log_id"], int(ts))
+                    if key not in self.store and key not in asked:
+                        asked.add(key)
+                        pool.submit(sweep_io.decode_sweep_columns, Path(seq["log_dir"]) / "sensors" / "lidar" / f"{ts}.feather")
+
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            n_batches = (len(order) + batch_size - 1) // batch_size
+            for b in range(min(ahead, n_batches)):
+                request(pool, b)
+            for b, batch in enumerate(inner):
+                if b + ahead < n_batches:
+                    request(pool, b + ahead)
+                if len(asked) > 4096:
+                    asked.clear()
+                yield batch
