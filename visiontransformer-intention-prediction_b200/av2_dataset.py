@@ -23,7 +23,7 @@ from typing import Callable, Iterator, List, Optional
 
 import numpy as np
 
-from . import dataset_shim, map_ops, maps, sweep_io, sweep_store
+from . import bev_ops, dataset_shim, map_ops, maps, pose, sweep_io, sweep_store
 from .constants import LIDAR_SWEEPS
 
 
@@ -67,6 +67,14 @@ def make_sequences(scenarios: List[dict], num_sweeps: int = LIDAR_SWEEPS) -> Lis
     return seqs
 
 
+class _Sample:
+    """what Av2BevDataset hands to BevBatchLoader: ``store_frame`` (sweeps named in the store), ``map_index``, ``gt``"""
+    store_frame = None
+    map_index = 0
+    gt = None
+    sequence = None
+
+
 class _LazySamples:
     """Sequence view BevBatchLoader slices: sample i is decoded when its batch is built."""
 
@@ -92,6 +100,7 @@ class Av2BevDataset:
         if not self.sequences:
             raise ValueError(f"Could not create any valid sequences from the provided scenarios in {data_dir}.")     # dataset.py:171
         self._poses = {}
+        self._no_sweep = set()
         self._map_index = {sc["log_id"]: k for k, sc in enumerate(self.scenarios)}
         self.map_table = map_ops.MapTable([self._load_map(sc["map_json_path"]) for sc in self.scenarios], device=device)
         self.store = sweep_store.SweepStore(store_points, device=self.map_table.device)
@@ -107,27 +116,79 @@ class Av2BevDataset:
     def __len__(self) -> int:
         return len(self.sequences)
 
-    def _ego_poses(self, seq: dict):
-        df = self._poses.get(seq["log_id"])
-        if df is None:
+    def _log_poses(self, seq: dict) -> dict:
+        """timestamp -> float64 [7] (tx,ty,tz,qx,qy,qz,qw) of the log's FIRST pose row with that timestamp (what the
+        reference's ``df[df.timestamp_ns == ts].iloc[0]`` picks, dataset.py:285-289,323-327), or ``None`` when scipy rejects
+        the quaternion (dataset.py:293-296,330-334).  Built once per log instead of one pandas scan per lookup."""
+        table = self._poses.get(seq["log_id"])
+        if table is None:
             import pyarrow.feather as feather
             df = feather.read_feather(Path(seq["log_dir"]) / "city_SE3_egovehicle.feather")    # utils.py:22-25
-            self._poses[seq["log_id"]] = df
-        return df
+            cols = np.stack([df[c].to_numpy(np.float64) for c in ("tx_m", "ty_m", "tz_m", "qx", "qy", "qz", "qw")], 1)
+            table = {}
+            for t, row in zip(df["timestamp_ns"].to_numpy().tolist(), cols):
+                if t in table:
+                    continue
+                try:
+                    pose.se3_from_pose(row[:3], row[3:7])
+                    table[t] = row
+                except ValueError:
+                    table[t] = None
+            self._poses[seq["log_id"]] = table
+        return table
+
+    def _resident(self, seq: dict, ts: int):
+        """store key of sweep ``ts`` (decoded and uploaded on first use), or ``None`` for the reference's "skip this sweep"
+        cases: file missing / empty table / unreadable (dataset.py:307-318)."""
+        key = (seq["log_id"], int(ts))
+        if key in self.store:
+            return key
+        if key in self._no_sweep:
+            return None
+        path = Path(seq["log_dir"]) / "sensors" / "lidar" / f"{ts}.feather"
+        cols = sweep_io.decode_sweep_columns(path)
+        if cols is sweep_io.NOT_COLUMNAR:                                 # other dtypes on disk: split the rows losslessly (or raise)
+            rows = sweep_io.decode_sweep(path)
+            pc = bev_ops.PointColumns.from_points4(rows.astype(np.float32), pinned=False)
+            h, st, n = pc.buf.numpy(), pc.stride, pc.n
+            cols = tuple(h[2 * j * st:2 * j * st + 2 * n].view(np.float16) for j in range(3)) + (h[6 * st:6 * st + n],)
+        if cols is None:
+            self._no_sweep.add(key)
+            return None
+        self.store.put(key, *cols)
+        return key
 
     def sample(self, idx: int):
-        """dataset.py:262-345 up to the hot path: the sample's sweeps (AV2 columns) and poses, or ``None`` where the reference
-        returns ``None``."""
+        """dataset.py:262-345 up to the hot path, or ``None`` where the reference returns ``None`` (no current pose row
+        :286-287, invalid current quaternion :294-296, every sweep missing :344-345).  The sample names its sweeps in the
+        store (``store_frame``); nothing is concatenated or re-uploaded."""
         seq = self.sequences[idx]
-        fr = sweep_io.load_frame(seq["log_dir"], seq["sweep_ts_list"], seq["current_ts_ns"], self._ego_poses(seq), layout="columns")
-        if fr is None:
+        poses = self._log_poses(seq)
+        cur = poses.get(seq["current_ts_ns"])
+        if cur is None:
+            if seq["current_ts_ns"] in poses:
+                print(f"Warning: Invalid quaternion for ego pose at ts {seq['current_ts_ns']} in log {seq['log_id']}. Skipping item.")
             return None
-        fr.sweep_keys = [(seq["log_id"], int(ts)) for ts in seq["sweep_ts_list"]]
-        fr.map_index = self._map_index[seq["log_id"]]
-        fr.sequence = seq
-        if self.gt_of is not None:
-            fr.gt = self.gt_of(seq)
-        return fr
+        S = len(seq["sweep_ts_list"])
+        keys: List[Optional[tuple]] = [None] * S
+        sp = np.zeros((S, 7), np.float64)
+        sp[:, 6] = 1.0                                                   # identity for missing sweeps (never used: no points)
+        for k, ts in enumerate(seq["sweep_ts_list"]):
+            prow = poses.get(ts)                                         # dataset.py:323-334: no / invalid pose row -> None sweep
+            if prow is None:                                             # (checked before the file: such a sweep is never uploaded)
+                continue
+            key = self._resident(seq, ts)
+            if key is None:
+                continue
+            keys[k], sp[k] = key, prow
+        if all(k is None for k in keys):
+            return None
+        out = _Sample()
+        out.store_frame = sweep_store.StoreFrame(keys, sp, cur)
+        out.map_index = self._map_index[seq["log_id"]]
+        out.sequence = seq
+        out.gt = self.gt_of(seq) if self.gt_of is not None else None
+        return out
 
     def loader(self, batch_size: int = 8, shuffle: bool = False, rng: Optional[np.random.Generator] = None,
                drop_last: bool = False, decode_threads: int = 0, decode_ahead: int = 2) -> Iterator[dict]:

@@ -86,6 +86,9 @@ class BevBatchLoader:
         from . import sweep_store as ss
         frames = []
         for smp in chunk:
+            if getattr(smp, "store_frame", None) is not None:        # the sample already names its sweeps in the store
+                frames.append(smp.store_frame)
+                continue
             off = np.asarray(smp.sweep_offsets)
             cols = getattr(smp, "columns", None)
             keys = list(smp.sweep_keys)
@@ -119,7 +122,8 @@ class BevBatchLoader:
                 if not self.keep_order:      # frames that rotate / scale first: no identity copies (order is returned)
                     chunk, aug, _ = pipeline.partition_for_augmentation(chunk, aug)
             ids = [self.map_id_of(s) for s in chunk] if self.with_map else None
-            if self.store is not None and all(getattr(s, "sweep_keys", None) is not None for s in chunk):
+            if self.store is not None and all(getattr(s, "store_frame", None) is not None or
+                                              getattr(s, "sweep_keys", None) is not None for s in chunk):
                 fb = self._pack_from_store(chunk, ids)
             else:
                 fb = pipeline.FrameBatch.pack(chunk, self.S, map_ids=ids)
