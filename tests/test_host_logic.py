@@ -208,3 +208,27 @@ def test_sweep_store_ring_allocation_and_pins():
     assert put(4, 20) == 0 and 2 not in s._entries and not s._pins
     with pytest.raises(ValueError):
         s._alloc(72)
+
+
+def test_sweep_store_ring_never_overlaps_live_sweeps():
+    """random put sequences against the allocator: live sweeps never share rows, rows stay 8-aligned and inside the ring"""
+    import collections
+    from hypothesis import given, settings, strategies as st
+    from bevgen_b200.sweep_store import SweepStore
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(min_value=0, max_value=70), min_size=1, max_size=60), st.integers(min_value=80, max_value=400))
+    def run(sizes, cap):
+        s = SweepStore.__new__(SweepStore)
+        s.capacity, s._entries, s._head, s._epoch, s._events = (cap + 7) // 8 * 8, collections.OrderedDict(), 0, 0, {}
+        s._last_use, s._pins, s._wait_epoch, s.evictions = {}, collections.Counter(), 0, 0
+        for k, n in enumerate(sizes):
+            need = max(8, (n + 7) // 8 * 8)
+            r = s._alloc(need)
+            s._entries[k] = (r, n)
+            assert r % 8 == 0 and 0 <= r and r + need <= s.capacity
+            spans = sorted((row, row + max(8, (m + 7) // 8 * 8)) for row, m in s._entries.values())
+            assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])), spans
+            assert k in s._entries
+
+    run()

@@ -240,3 +240,23 @@ def test_av2_column_points(bg, co, algo):
     f.points4[5, 3] = 0.5
     with pytest.raises(ValueError):
         bg.FrameBatch.pack([f], S, points_dtype="av2")                                       # intensity not a uint8 value
+
+
+def test_av2_columns_non_finite_and_extreme_values(bg, co):
+    """float16 columns can hold NaN, +-inf and +-65504: such points are masked exactly as the reference masks them
+    (utils.py:83-87 on the float64 values), bin-edge coordinates that ARE float16 values land in the reference's voxel"""
+    rng = np.random.default_rng(5)
+    n = 4096
+    p = np.empty((n, 4), np.float32)
+    p[:, 0] = rng.choice((60.0 - 0.25 * np.arange(-8, 330)).astype(np.float16).astype(np.float32), n)     # multiples of 0.25: exact in fp16
+    p[:, 1] = rng.choice((-72.0 + 0.25 * np.arange(-8, 590)).astype(np.float16).astype(np.float32), n)
+    p[:, 2] = rng.choice((-2.0 + 0.125 * np.arange(-4, 52)).astype(np.float16).astype(np.float32), n)
+    p[:, 3] = rng.integers(0, 256, n)
+    p[:16, 0] = np.nan; p[16:32, 1] = np.inf; p[32:48, 2] = -np.inf; p[48:64, 0] = 65504.0; p[64:80, 1] = -65504.0
+    off = np.array([0, n], np.int32)
+    want = co.lidar_bev_fused(p, off, np.eye(4)[None], 1)
+    assert np.count_nonzero(want) > 1000
+    pc = bg.PointColumns.from_points4(p)
+    for algo in (0, 1):
+        got = bg.lidar_bev_from_sweeps(pc, off, np.eye(4)[None], 1, 1, algo=algo)[0].cpu().numpy()
+        assert np.array_equal(got, want), algo
