@@ -239,7 +239,7 @@ def run_ours(args) -> None:
 
     wl = WORKLOADS[args.workload]
     B = args.batch or wl["batch"]
-    algo = {"atomic": bg.ALGO_ATOMIC, "tiled": bg.ALGO_TILED, "memset": bg.ALGO_MEMSET_ATOMIC}[args.algo]
+    algo = {"auto": bg.ALGO_AUTO, "atomic": bg.ALGO_ATOMIC, "tiled": bg.ALGO_TILED, "memset": bg.ALGO_MEMSET_ATOMIC}[args.algo]
     frames, md = make_frames(args.workload, B, args.points, rank)
     if args.points_dtype != "f32":
         frames = [bg.synthetic.quantize_f16(f) for f in frames]
@@ -458,7 +458,7 @@ def run_ours(args) -> None:
         "k_zero_fill_tma": LIDAR_FRAME_BYTES, "cudaMemsetAsync": LIDAR_FRAME_BYTES, "k_scatter_atomic": pts_frame * pbytes,
         "k_bin_fixed": pts_frame * pbytes, "k_tile_store": LIDAR_FRAME_BYTES, "k_overflow_red": 0,
         "k_map_expand": MAP_FRAME_BYTES, "k_augment": 2 * (LIDAR_FRAME_BYTES + (MAP_FRAME_BYTES if wl["map"] else 0)),
-        "k_tile_aug": LIDAR_FRAME_BYTES, "k_rebin_aug": 0,
+        "k_tile_aug": LIDAR_FRAME_BYTES, "k_rebin_aug": 0, "k_overflow_total": 0,
     }
     n_gather = sum(1 for p in (aug or []) if p.needs_gather)
     fused_aug = bool(aug) and "k_tile_aug" in kernels
@@ -548,7 +548,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", default="tiled", choices=["atomic", "tiled", "memset"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "atomic", "tiled", "memset"],
+                    help="auto (default): tiled, switching to atomic while the scenes keep overflowing the tile bins (config 4)")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--points", type=int, default=100_000, help="points per sweep")
     ap.add_argument("--points-dtype", default="av2", choices=["av2", "f16", "f32"],

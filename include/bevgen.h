@@ -40,6 +40,7 @@ extern "C" {
 #define BEVGEN_ALGO_TILED 0
 #define BEVGEN_ALGO_ATOMIC 1
 #define BEVGEN_ALGO_MEMSET_ATOMIC 2
+/* (the Python layer adds ALGO_AUTO = 3: TILED, switching to ATOMIC while the scenes keep overflowing the tile bins) */
 
 #define BEVGEN_E_INVALID_ARG (-1)
 #define BEVGEN_E_WORKSPACE   (-2)
@@ -100,6 +101,12 @@ int bevgen_transform_points_f64(const double *pts, int64_t n, int64_t stride, co
  *       All produce identical bits; a workspace is needed for TILED only.
  * ------------------------------------------------------------------------------------- */
 size_t bevgen_lidar_workspace_bytes(int64_t total_points, int B, int S);
+
+/* records the last BEVGEN_ALGO_TILED launch that used `workspace` (same total_points, B, S) sent to its overflow lists, summed
+ * into the device word out_dev on `stream`: dense / skewed scenes (most records overflowing their 128-slot tile bins) run faster
+ * on BEVGEN_ALGO_ATOMIC, and this is what a caller needs to notice (the Python layer's ALGO_AUTO does) */
+int bevgen_lidar_overflow_total(const void *workspace, size_t workspace_bytes, int64_t total_points, int B, int S,
+                                uint32_t *out_dev, bevgen_stream_t stream);
 
 int bevgen_lidar_bev_fused(const float *pts4, const int32_t *sweep_offsets, const double *rel_tf,
                            int B, int S, int64_t total_points, int max_sweep_points,

@@ -129,3 +129,31 @@ def test_generator_on_non_current_device(bg, co):
         wa = np.ascontiguousarray(co.scale(co.rotate(want, 3.0), 1.02))
         ga = gen.generate(batch, aug, with_map=False)["lidar_bev"]
         assert torch.equal(ga[0].cpu(), torch.from_numpy(wa))
+
+
+def test_algo_auto_switches_on_dense_scenes_and_back(bg, co):
+    """ALGO_AUTO: tiled for ordinary scenes; clustered scenes (most records overflow the 128-slot tile bins) flip it to the
+    atomic scatter after the first probed call, sparse ones flip it back; bits identical throughout"""
+    S = 10
+    dense = [bg.synthetic.frame_c4(i, n=30_000) for i in range(2)]
+    sparse = [bg.synthetic.frame_c2(i, n=30_000) for i in range(2)]
+    wd = np.stack([co.lidar_bev_fused(f.points4, f.sweep_offsets, f.rel_tf, S) for f in dense])
+    wsp = np.stack([co.lidar_bev_fused(f.points4, f.sweep_offsets, f.rel_tf, S) for f in sparse])
+    gen = bg.BevGenerator(algo=bg.ALGO_AUTO)
+    bd, bs = bg.FrameBatch.pack(dense, S), bg.FrameBatch.pack(sparse, S)
+    assert gen._auto["algo"] == bg.ALGO_TILED
+    for _ in range(3):
+        out = gen.generate(bd, with_map=False)["lidar_bev"]
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), wd)
+    assert gen._auto["algo"] == bg.ALGO_ATOMIC
+    assert gen.algo == bg.ALGO_AUTO
+    for _ in range(40):                                         # the 32nd call re-probes with the tiled path
+        out = gen.generate(bs, with_map=False)["lidar_bev"]
+        torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), wsp)
+    assert gen._auto["algo"] == bg.ALGO_TILED
+    # frames that are resampled always take the tile bins (the fused augmentation kernels read them)
+    aug = [bg.AugParams(angle_deg=4.0), bg.AugParams()]
+    ga = gen.generate(bd, aug, with_map=False)["lidar_bev"].cpu().numpy()
+    assert np.array_equal(ga[0], co.rotate(wd[0], 4.0)) and np.array_equal(ga[1], wd[1])

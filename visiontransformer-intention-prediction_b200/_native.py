@@ -66,6 +66,7 @@ PROTOTYPES = {
     "bevgen_transform_points_f32": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "bevgen_transform_points_f64": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "bevgen_lidar_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "bevgen_lidar_overflow_total": (_i, [_p, _sz, _i64, _i, _i, _p, _p]),
     "bevgen_lidar_bev_fused": (_i, [_p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),
     "bevgen_lidar_bev_fused_f16": (_i, [_p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),
     "bevgen_lidar_bev_fused_cols": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p]),

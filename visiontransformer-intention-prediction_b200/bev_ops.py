@@ -31,7 +31,8 @@ from .constants import (GRID_HEIGHT_PX, GRID_WIDTH_PX, LIDAR_HEIGHT_CHANNELS, LI
 #                     __match_any_sync-aggregated atomicMax, ONE TMA bulk store (each output byte written once)
 #   ATOMIC            TMA zero-fill kernel + one global RED.MAX scatter kernel (faster on dense / skewed scenes)
 #   MEMSET_ATOMIC     cudaMemsetAsync + the same scatter kernel (library fill, comparison point only)
-ALGO_TILED, ALGO_ATOMIC, ALGO_MEMSET_ATOMIC = 0, 1, 2
+#   AUTO              (pipeline.BevGenerator only) TILED, switching to ATOMIC while the scenes keep overflowing the tile bins
+ALGO_TILED, ALGO_ATOMIC, ALGO_MEMSET_ATOMIC, ALGO_AUTO = 0, 1, 2, 3
 MAX_DROP_RECTS = 5
 
 
@@ -333,6 +334,23 @@ def lidar_bev_from_sweeps(points4, sweep_offsets, rel_tf, num_frames: int, num_s
                     _ptr(f), _ptr(r), _ptr(c), _ptr(out), _ptr(ws), wbytes, int(algo), _stream_ptr())
     _native.check(rc, "bevgen_lidar_bev_fused")
     return out
+
+
+def overflow_total_async(total_points: int, num_frames: int, num_sweeps: int, device: torch.device):
+    """After a TILED ``lidar_bev_from_sweeps`` call on the current stream: (pinned int32 tensor, event) -- once the event has
+    completed the tensor holds the number of records that call sent to its overflow lists."""
+    L = _native.lib()
+    with torch.cuda.device(device):
+        wbytes = int(L.bevgen_lidar_workspace_bytes(int(total_points), int(num_frames), int(num_sweeps)))
+        ws = workspace.get("lidar", wbytes, device)
+        word = torch.empty(1, dtype=torch.int32, device=device)
+        rc = L.bevgen_lidar_overflow_total(_ptr(ws), wbytes, int(total_points), int(num_frames), int(num_sweeps), _ptr(word), _stream_ptr())
+        _native.check(rc, "bevgen_lidar_overflow_total")
+        host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        host.copy_(word, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+    return host, ev
 
 
 def lidar_bev_from_ego_points(points3, intensity, sweep_offsets, num_frames: int, num_sweeps: int = LIDAR_SWEEPS, *,

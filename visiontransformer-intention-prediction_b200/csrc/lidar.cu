@@ -741,6 +741,32 @@ extern "C" int bevgen_debug_at_profile(unsigned long long* out16, int reset) {
 }
 #endif
 
+namespace bevgen { namespace {
+__global__ void __launch_bounds__(256) k_overflow_total(const uint32_t* __restrict__ ovf_cnt, int n, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    uint32_t v = 0;
+    for (int i = threadIdx.x; i < n; i += 256) v += ovf_cnt[i];
+    atomicAdd(&s, v);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = s;
+}
+} }
+
+// Number of records the last TILED launch on `workspace` (same total_points, B, S) sent to the overflow lists, written to
+// the device word out_dev on `stream`: what a caller needs to decide whether a scene is dense enough for ALGO_ATOMIC.
+extern "C" int bevgen_lidar_overflow_total(const void* workspace, size_t workspace_bytes, int64_t total_points, int B, int S,
+                                           uint32_t* out_dev, bevgen_stream_t stream) {
+    if (!workspace || !out_dev || total_points < 0 || B <= 0 || S <= 0) return BEVGEN_E_INVALID_ARG;
+    const TiledWorkspace L = tiled_layout(total_points, B, S);
+    if (workspace_bytes < L.bytes) return BEVGEN_E_WORKSPACE;
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(static_cast<const char*>(workspace) + L.cnt);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BEVGEN_LAUNCH("k_overflow_total", st, (k_overflow_total<<<1, 256, 0, st>>>(cnt + (size_t)B * S * kTilesPerSweep, B * S, out_dev)));
+    return 0;
+}
+
 extern "C" size_t bevgen_lidar_aug_workspace_bytes(int64_t total_points, int B, int S, int n_resampled) {
     if (total_points < 0 || B <= 0 || S <= 0 || n_resampled < 0 || n_resampled > B) return 0;
     return tiled_layout(total_points, B, S, n_resampled).bytes;

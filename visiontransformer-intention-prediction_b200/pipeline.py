@@ -134,6 +134,9 @@ class BevGenerator:
         # the grid) instead of generate -> gather (three passes over it).  Tiled algorithm only; same bits either way.
         self.fused_augment = fused_augment
         self._scratch = {}
+        # ALGO_AUTO: TILED until the scenes overflow the tile bins (dense / skewed point clouds: BASELINE config 4), then
+        # ATOMIC, re-probing with one TILED call every 32 batches; the overflow total comes back asynchronously (4 bytes)
+        self._auto = {"algo": bev_ops.ALGO_TILED, "pending": None, "calls": 0}
         # the map rasterizer is independent of the LiDAR kernels and far from saturating the GPU (one warp per lane
         # segment): it runs on a side stream and is joined before the tensors are handed out
         # (measured on config 3: default priority 16 700 frames/s; a high-priority map stream delays the binning pass: 16 440)
@@ -172,7 +175,36 @@ class BevGenerator:
         the rasterizer's bit planes) -- or, with ``fused_augment=False`` / parameters outside the fused kernel's reach,
         generated into scratch and resampled by the dense gather kernel.  Same bits either way."""
         with torch.cuda.device(self.device):      # the generator's device, whatever the caller's current device is
-            return self._generate(batch, aug, dev, with_map, out_lidar, out_map)
+            if self.algo != bev_ops.ALGO_AUTO:
+                return self._generate(batch, aug, dev, with_map, out_lidar, out_map)
+            resampling = aug is not None and any(p.needs_gather for p in aug)
+            self.algo = self._auto_pick(resampling)
+            try:
+                out = self._generate(batch, aug, dev, with_map, out_lidar, out_map)
+                if self.algo == bev_ops.ALGO_TILED and not resampling and batch.num_points > 0 and self._auto["calls"] % 8 == 1:
+                    # (every 8th TILED call is probed; batches with resampled frames lay their workspace out differently)
+                    host, ev = bev_ops.overflow_total_async(batch.num_points, batch.num_frames, batch.num_sweeps, self.device)
+                    self._auto["pending"] = (host, ev, batch.num_points)
+                return out
+            finally:
+                self.algo = bev_ops.ALGO_AUTO
+
+    def _auto_pick(self, resampling: bool) -> int:
+        """ALGO_AUTO policy.  Overflow fraction of the last probed TILED call > 25 % -> ATOMIC (config 4: ~90 %), < 10 % ->
+        TILED (config 2: 0.6 %); frames that are resampled need the tile bins; every 32nd call re-probes with TILED."""
+        st = self._auto
+        st["calls"] += 1
+        if st["pending"] is not None and st["pending"][1].query():
+            host, _, n = st["pending"]
+            frac = float(host.item()) / max(1, n)
+            st["pending"] = None
+            if frac > 0.25:
+                st["algo"] = bev_ops.ALGO_ATOMIC
+            elif frac < 0.10:
+                st["algo"] = bev_ops.ALGO_TILED
+        if resampling or st["calls"] % 32 == 0:
+            return bev_ops.ALGO_TILED
+        return st["algo"]
 
     def _generate(self, batch, aug, dev, with_map, out_lidar, out_map) -> dict:
         B, S = batch.num_frames, batch.num_sweeps
