@@ -178,20 +178,21 @@ class BevGenerator:
             if self.algo != bev_ops.ALGO_AUTO:
                 return self._generate(batch, aug, dev, with_map, out_lidar, out_map)
             resampling = aug is not None and any(p.needs_gather for p in aug)
-            self.algo = self._auto_pick(resampling)
+            self.algo, probe = self._auto_pick(resampling)
             try:
                 out = self._generate(batch, aug, dev, with_map, out_lidar, out_map)
-                if self.algo == bev_ops.ALGO_TILED and not resampling and batch.num_points > 0 and self._auto["calls"] % 8 == 1:
-                    # (every 8th TILED call is probed; batches with resampled frames lay their workspace out differently)
+                if probe and batch.num_points > 0:
                     host, ev = bev_ops.overflow_total_async(batch.num_points, batch.num_frames, batch.num_sweeps, self.device)
                     self._auto["pending"] = (host, ev, batch.num_points)
                 return out
             finally:
                 self.algo = bev_ops.ALGO_AUTO
 
-    def _auto_pick(self, resampling: bool) -> int:
-        """ALGO_AUTO policy.  Overflow fraction of the last probed TILED call > 25 % -> ATOMIC (config 4: ~90 %), < 10 % ->
-        TILED (config 2: 0.6 %); frames that are resampled need the tile bins; every 32nd call re-probes with TILED."""
+    def _auto_pick(self, resampling: bool):
+        """ALGO_AUTO policy -> (algorithm of this call, probe its overflow total?).  Overflow fraction of the last probed TILED
+        call > 25 % -> ATOMIC (config 4: ~90 %), < 10 % -> TILED (config 2: 0.6 %).  While TILED every 8th call is probed;
+        while ATOMIC every 32nd call runs TILED to re-probe.  Batches with resampled frames always run TILED (the fused
+        augmentation kernels read the tile bins) and are not probed (their workspace is laid out differently)."""
         st = self._auto
         st["calls"] += 1
         if st["pending"] is not None and st["pending"][1].query():
@@ -202,9 +203,13 @@ class BevGenerator:
                 st["algo"] = bev_ops.ALGO_ATOMIC
             elif frac < 0.10:
                 st["algo"] = bev_ops.ALGO_TILED
-        if resampling or st["calls"] % 32 == 0:
-            return bev_ops.ALGO_TILED
-        return st["algo"]
+        if resampling:
+            return bev_ops.ALGO_TILED, False
+        if st["algo"] == bev_ops.ALGO_TILED:
+            return bev_ops.ALGO_TILED, st["calls"] % 8 == 1
+        if st["calls"] % 32 == 0:
+            return bev_ops.ALGO_TILED, True
+        return st["algo"], False
 
     def _generate(self, batch, aug, dev, with_map, out_lidar, out_map) -> dict:
         B, S = batch.num_frames, batch.num_sweeps
