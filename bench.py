@@ -38,6 +38,8 @@ MAP_FRAME_BYTES = 9 * 400 * 720 * 4          # 10 368 000
 FALLBACK_HBM_GBS = 6650.0                    # /opt/skills/guides/B200_PROFILING.md fallback
 
 WORKLOADS = {
+    "c1": dict(desc="configs[0]: the reference's CPU-runnable case: one frame, ONE loaded sweep of 100k pts (output still 290 channels)",
+               batch=1, map=False, aug=False, loaded_sweeps=1),
     "c2": dict(desc="configs[1]: multi-sweep aggregation, 10 sweeps x 100k pts, synthetic ego poses", batch=32, map=False, aug=False),
     "c3": dict(desc="configs[2]: LiDAR + HD-map rasterized channels (425 lanes, 20 crosswalks)", batch=32, map=True, aug=False),
     "c4": dict(desc="configs[3]: dense/skewed scene, 1M pts/frame in 4 clusters", batch=32, map=False, aug=False),
@@ -53,7 +55,9 @@ def make_frames(workload: str, batch: int, points: int, rank: int):
     frames = []
     for i in range(batch):
         idx = rank * batch + i
-        if workload == "c2":
+        if workload == "c1":
+            frames.append(syn.frame_c1(idx, n=points))
+        elif workload == "c2":
             frames.append(syn.frame_c2(idx, n=points))
         elif workload == "c4":
             frames.append(syn.frame_c4(idx, n=points))
@@ -74,9 +78,10 @@ def workload_config(args) -> dict:
     wl = WORKLOADS[args.workload]
     B = args.batch or wl["batch"]
     pb = POINT_FORMATS[args.points_dtype][0]
-    inputs_mb = B * 10 * args.points * pb / 1e6
-    return {"workload": wl["desc"], "batch_per_gpu": B, "sweeps": 10, "points_per_sweep": args.points,
-            "points_per_frame": 10 * args.points, "points_format": POINT_FORMATS[args.points_dtype][1],
+    loaded = wl.get("loaded_sweeps", 10)
+    inputs_mb = B * loaded * args.points * pb / 1e6
+    return {"workload": wl["desc"], "batch_per_gpu": B, "sweeps": 10, "loaded_sweeps": loaded, "points_per_sweep": args.points,
+            "points_per_frame": loaded * args.points, "points_format": POINT_FORMATS[args.points_dtype][1],
             "point_values": "synthetic float32 draws" + ("" if args.points_dtype == "f32" else
                                                          " rounded to float16-representable coordinates (same values on both arms)"),
             "arithmetic": "float64 pose transform and binning, float32 intensities (the reference's own precision and op order)",
@@ -100,7 +105,8 @@ def _cpu_worker(args):
     import bevgen_b200 as bg
     from oracle import numpy_port as npp
     syn = bg.synthetic
-    f = syn.frame_c4(idx, n=points) if workload == "c4" else (syn.frame_c2(idx, n=points) if workload == "c2" else syn.frame_c3(idx, n=points, map_data={}))
+    f = syn.frame_c1(idx, n=points) if workload == "c1" else syn.frame_c4(idx, n=points) if workload == "c4" else \
+        (syn.frame_c2(idx, n=points) if workload == "c2" else syn.frame_c3(idx, n=points, map_data={}))
     if quantize:
         f = syn.quantize_f16(f)          # the same point values our arm consumes
     t0 = time.perf_counter()
@@ -159,7 +165,7 @@ def run_reference(args) -> None:
     wl = WORKLOADS[args.workload]
     fps, step_s, nsteps = cpu_reference(args.workload, args.points, args.steps, args.warmup, workers,
                                         quantize=args.points_dtype != "f32")
-    pts_frame = 10 * args.points
+    pts_frame = wl.get("loaded_sweeps", 10) * args.points
     line = {
         "impl": "reference", "metric": "bev_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": nsteps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -362,15 +368,16 @@ def run_ours(args) -> None:
     # ---- end to end through the host-facing API -----------------------------------------------------------
     # strict reference signature (numpy lists in -> fresh numpy array out, one frame per call): includes the 334 MB D2H
     strict_fps = None
-    if world == 1 and args.workload in ("c2", "c4"):
+    if world == 1 and args.workload in ("c1", "c2", "c4"):
         f0 = frames[0]
-        pl = [bg.transform_points(f0.sweep(s)[:, :3], f0.rel_tf[s]) for s in range(S)]
-        il = [f0.sweep(s)[:, 3].copy() for s in range(S)]
+        S0 = f0.num_sweeps
+        pl = [bg.transform_points(f0.sweep(s)[:, :3], f0.rel_tf[s]) for s in range(S0)]
+        il = [f0.sweep(s)[:, 3].copy() for s in range(S0)]
         for _ in range(2):                          # warm-up: the pinned result buffers are allocated once, then recycled
             bg.create_intentnet_lidar_bev(pl, il)
         t0 = time.perf_counter()
         for _ in range(6):
-            pl = [bg.transform_points(f0.sweep(s)[:, :3], f0.rel_tf[s]) for s in range(S)]
+            pl = [bg.transform_points(f0.sweep(s)[:, :3], f0.rel_tf[s]) for s in range(S0)]
             bg.create_intentnet_lidar_bev(pl, il)
         strict_fps = 6 / (time.perf_counter() - t0)
     # ---- sliding-window stream through the device-resident sweep store (AV2 columns only) --------------------------------
@@ -379,7 +386,7 @@ def run_ours(args) -> None:
     # copy stream) and named by the up to 10 samples that use it, so a step moves B new sweeps over PCIe instead of 10 B.
     # Same kernels, same per-frame work (every sample still transforms and bins all of its 10 sweeps).
     sw = None
-    if args.points_dtype == "av2" and not args.no_sliding_window:
+    if args.points_dtype == "av2" and not args.no_sliding_window and args.workload != "c1":
         sw = {}
         pool_n = 64                                                   # distinct synthetic sweeps, cycled (every key is a new upload)
         sweeps, poses = bg.synthetic.sliding_log(pool_n, n=args.points, seed=7 + rank, dense=args.workload == "c4")
