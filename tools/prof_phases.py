@@ -23,3 +23,6 @@ for name, p in {"rotate": bg.AugParams(angle_deg=9.0), "scale": bg.AugParams(sca
     lib.bevgen_debug_at_profile(buf, 1)
     n = buf[8] * 29
     print(name, "cycles per channel iteration (thread %s):" % sys.argv[2], " ".join(f"{nm}={buf[k]/n:.0f}" for k, nm in enumerate(names)), "total=%.0f" % (sum(buf[:8]) / n))
+    c = buf[8]
+    print(f"   per CTA: set-up to 1st barrier (global loads) {buf[9]/c:.0f}, to 2nd (geometry, taps) {buf[10]/c:.0f}, to the loop (tables, clearing) {buf[11]/c:.0f}; "
+          f"whole CTA {buf[12]/c:.0f} cycles -> set-up = {100*(buf[9]+buf[10]+buf[11])/buf[12]:.1f} %")

@@ -433,6 +433,10 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     __shared__ AugSlowArgs SA;
 
     const int tid = threadIdx.x;
+#ifdef BEVGEN_AT_PROFILE
+    const long long t_entry = clock64();
+    long long t_s1 = 0, t_s2 = 0;
+#endif
     const int tile = blockIdx.x, bx = tile % kATBX, by = tile / kATBX, sweep = blockIdx.y;
     const int fsrc = fl.src[blockIdx.z], fdst = fl.dst[blockIdx.z], slot = fl.slot[blockIdx.z];
     const int ox0 = bx * kATW, oy0 = by * kATH;
@@ -454,6 +458,9 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     if (SCL && tid < 80) { T.xf[tid] = 127; T.xl[tid] = -1; if (tid < 48) { T.yf[tid] = 127; T.yl[tid] = -1; } }
     static_assert(kATThreads >= kATW + kATH + 32 && kATThreads >= 80, "one thread per table entry");
     __syncthreads();
+#ifdef BEVGEN_AT_PROFILE
+    t_s1 = clock64();
+#endif
     int nrect = P.n_rects;
     nrect = nrect > kMaxRects ? kMaxRects : (nrect < 0 ? 0 : nrect);
 
@@ -478,6 +485,9 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
         else     { T.s0y[l] = (short)s0; T.s1y[l] = (short)s1; T.wy0[l] = w0; T.wy1[l] = w1; }
     }
     __syncthreads();
+#ifdef BEVGEN_AT_PROFILE
+    t_s2 = clock64();
+#endif
     if (G.FW * G.FH > Cfg::kT0 || G.FW > 127 || G.FH > 127 || G.QW > 80 || G.QH > 48 || (ROT && (G.DW > Cfg::kDW || G.DH > Cfg::kDH)) ||
         (ROT && SCL && G.DW * G.DH > Cfg::kT1) || (ROT && (RF.hx >= 1.5f || RF.hy >= 1.5f)))
         __trap();
@@ -521,6 +531,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
 #ifdef BEVGEN_AT_PROFILE
     constexpr int PROF_TID = BEVGEN_AT_PROFILE;
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+    const long long t_loop = tprev;
 #endif
 #pragma unroll 1
     for (int z = 0; z < kZ; ++z) {
@@ -617,7 +628,15 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
     }
     if (tid == 0) bulk_wait_read<0>();                        // shared memory must outlive the last copies' reads
 #ifdef BEVGEN_AT_PROFILE
-    if (tid == PROF_TID) { for (int k = 0; k < 8; ++k) atomicAdd(&g_at_prof[k], (unsigned long long)prof[k]); atomicAdd(&g_at_prof[8], 1ull); }
+    if (tid == PROF_TID) {
+        for (int k = 0; k < 8; ++k) atomicAdd(&g_at_prof[k], (unsigned long long)prof[k]);
+        atomicAdd(&g_at_prof[8], 1ull);
+        // set-up: entry -> parameters / counts loaded (first barrier) -> geometry + taps (second) -> tables + cleared tiles (loop)
+        atomicAdd(&g_at_prof[9], (unsigned long long)(t_s1 - t_entry));
+        atomicAdd(&g_at_prof[10], (unsigned long long)(t_s2 - t_s1));
+        atomicAdd(&g_at_prof[11], (unsigned long long)(t_loop - t_s2));
+        atomicAdd(&g_at_prof[12], (unsigned long long)(clock64() - t_entry));
+    }
 #endif
 }
 
