@@ -3,7 +3,7 @@ the serving / eval case (is_train=False).  Plain calls vs the CUDA-graph replay 
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-import numpy as np, torch
+import torch
 import bevgen_b200 as bg
 
 with_map = len(sys.argv) > 1 and sys.argv[1] == "map"

@@ -14,7 +14,7 @@
 from __future__ import annotations
 
 import random
-from typing import Callable, Iterable, Iterator, List, Optional, Sequence
+from typing import Callable, Iterator, List, Optional, Sequence
 
 import numpy as np
 import torch

@@ -11,7 +11,7 @@ reference (dataset.py:262-361, :137-150), as a handful of kernel launches per ba
 from __future__ import annotations
 
 import dataclasses
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch

@@ -18,7 +18,7 @@ import collections
 import dataclasses
 import threading
 from pathlib import Path
-from typing import Dict, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 
