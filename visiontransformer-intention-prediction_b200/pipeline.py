@@ -176,17 +176,14 @@ class BevGenerator:
         generated into scratch and resampled by the dense gather kernel.  Same bits either way."""
         with torch.cuda.device(self.device):      # the generator's device, whatever the caller's current device is
             if self.algo != bev_ops.ALGO_AUTO:
-                return self._generate(batch, aug, dev, with_map, out_lidar, out_map)
+                return self._generate(batch, aug, dev, with_map, out_lidar, out_map, self.algo)
             resampling = aug is not None and any(p.needs_gather for p in aug)
-            self.algo, probe = self._auto_pick(resampling)
-            try:
-                out = self._generate(batch, aug, dev, with_map, out_lidar, out_map)
-                if probe and batch.num_points > 0:
-                    host, ev = bev_ops.overflow_total_async(batch.num_points, batch.num_frames, batch.num_sweeps, self.device)
-                    self._auto["pending"] = (host, ev, batch.num_points)
-                return out
-            finally:
-                self.algo = bev_ops.ALGO_AUTO
+            algo, probe = self._auto_pick(resampling)
+            out = self._generate(batch, aug, dev, with_map, out_lidar, out_map, algo)
+            if probe and batch.num_points > 0:
+                host, ev = bev_ops.overflow_total_async(batch.num_points, batch.num_frames, batch.num_sweeps, self.device)
+                self._auto["pending"] = (host, ev, batch.num_points)
+            return out
 
     def _auto_pick(self, resampling: bool):
         """ALGO_AUTO policy -> (algorithm of this call, probe its overflow total?).  Overflow fraction of the last probed TILED
@@ -211,7 +208,7 @@ class BevGenerator:
             return bev_ops.ALGO_TILED, True
         return st["algo"], False
 
-    def _generate(self, batch, aug, dev, with_map, out_lidar, out_map) -> dict:
+    def _generate(self, batch, aug, dev, with_map, out_lidar, out_map, algo: int) -> dict:
         B, S = batch.num_frames, batch.num_sweeps
         dv = dev if dev is not None else self.upload(batch)
         flip = rects = cnt = None
@@ -222,7 +219,7 @@ class BevGenerator:
                 raise ValueError("one AugParams per frame")
             need = [p.needs_gather for p in aug]
             J = sum(need)
-            if J and self.fused_augment and self.algo == bev_ops.ALGO_TILED:
+            if J and self.fused_augment and algo == bev_ops.ALGO_TILED:
                 packed = _aug.pack_params(aug)
                 if not _aug.fused_supported(aug, packed):
                     packed = None               # parameters outside the fused kernel's reach: dense route
@@ -257,7 +254,7 @@ class BevGenerator:
                                           hi - lo, S, max_sweep_points=batch.max_sweep_points,
                                           flip=None if d_flip is None else d_flip[sl],
                                           drop_rects=None if d_rects is None else d_rects[sl],
-                                          drop_counts=None if d_cnt is None else d_cnt[sl], out=dst_l, algo=self.algo,
+                                          drop_counts=None if d_cnt is None else d_cnt[sl], out=dst_l, algo=algo,
                                           sweep_start=None if d_start is None else d_start[lo * S:hi * S], **skw)
             if with_map:
                 with torch.cuda.stream(self._map_stream):

@@ -40,7 +40,7 @@ class SweepStore:
     rows first waits for the event of the sweep's last epoch -- not for the newest kernels, so uploads for step i+1 still
     overlap the kernels of step i.  Capacity must cover the sweeps of the batches in flight: a batch whose sweep is gone
     fails in ``StoreBatch.pack`` (KeyError), and an upload that would overwrite a pinned sweep raises -- never silently
-    wrong."""
+    wrong.  Not thread-safe: one store per loader thread (decode in worker threads, ``put`` on the thread that launches)."""
 
     def __init__(self, capacity_points: int, device: Optional[torch.device] = None) -> None:
         self.device = torch.device(device) if device is not None else bev_ops._require_cuda()
