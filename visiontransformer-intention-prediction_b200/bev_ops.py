@@ -227,7 +227,7 @@ class _PinnedPool:
         buf = self.take(nbytes)
         host = buf.view(t.dtype).reshape(t.shape)
         host.copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(t.device).synchronize()        # the tensor's device, which need not be the current one
         arr = host.numpy()
         weakref.finalize(arr, self._release, buf)     # numpy views keep `arr` alive through .base, so this fires last
         return arr

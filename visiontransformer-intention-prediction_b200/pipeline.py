@@ -319,7 +319,7 @@ class PrefetchingGenerator:
 
     def run(self, handle, aug: Optional[Sequence[_aug.AugParams]] = None, **kw) -> dict:
         batch, dev, ev = handle
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream(self.gen.device)
         cur.wait_event(ev)
         store = getattr(batch, "store", None)
         for t in dev.values():
