@@ -117,7 +117,7 @@ def test_pinned_pool_never_aliases_live_results(monkeypatch):
             pass
 
     monkeypatch.setattr(pool, "take", take)
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda: _Stream())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
     t = torch.arange(1 << 19, dtype=torch.float32)
     a, b = pool.to_numpy(t), pool.to_numpy(t + 1)
     assert a.ctypes.data != b.ctypes.data and a[5] == 5 and b[5] == 6      # two live results: two buffers
