@@ -103,7 +103,19 @@ class Av2BevDataset:
         self._no_sweep = set()
         self._map_index = {sc["log_id"]: k for k, sc in enumerate(self.scenarios)}
         self.map_table = map_ops.MapTable([self._load_map(sc["map_json_path"]) for sc in self.scenarios], device=device)
-        self.store = sweep_store.SweepStore(store_points, device=self.map_table.device)
+        # AV2 stores float16 x,y,z + uint8 intensity; a directory with other dtypes (float32 exports) cannot live in the
+        # column store and goes through the row path instead (every sample packs and uploads its own ten sweeps)
+        self.columnar = all(self._probe_columnar(sc) for sc in self.scenarios)
+        self.store = sweep_store.SweepStore(store_points, device=self.map_table.device) if self.columnar else None
+        self._pose_frames = {}
+
+    @staticmethod
+    def _probe_columnar(sc: dict) -> bool:
+        for p in sorted((Path(sc["log_dir"]) / "sensors" / "lidar").glob("*.feather")):
+            cols = sweep_io.decode_sweep_columns(p, use_cache=False)
+            if cols is not None:                                         # first readable, non-empty sweep decides
+                return cols is not sweep_io.NOT_COLUMNAR
+        return True
 
     @staticmethod
     def _load_map(path: str) -> maps.FlatMap:
@@ -163,6 +175,8 @@ class Av2BevDataset:
         :286-287, invalid current quaternion :294-296, every sweep missing :344-345).  The sample names its sweeps in the
         store (``store_frame``); nothing is concatenated or re-uploaded."""
         seq = self.sequences[idx]
+        if not self.columnar:
+            return self._row_sample(seq)
         poses = self._log_poses(seq)
         cur = poses.get(seq["current_ts_ns"])
         if cur is None:
@@ -190,6 +204,21 @@ class Av2BevDataset:
         out.gt = self.gt_of(seq) if self.gt_of is not None else None
         return out
 
+    def _row_sample(self, seq: dict):
+        """non-AV2 dtypes on disk: the sample carries its own points as rows (sweep_io.load_frame), no store"""
+        df = self._pose_frames.get(seq["log_id"])
+        if df is None:
+            import pyarrow.feather as feather
+            df = feather.read_feather(Path(seq["log_dir"]) / "city_SE3_egovehicle.feather")
+            self._pose_frames[seq["log_id"]] = df
+        fr = sweep_io.load_frame(seq["log_dir"], seq["sweep_ts_list"], seq["current_ts_ns"], df, layout="rows")
+        if fr is None:
+            return None
+        fr.map_index = self._map_index[seq["log_id"]]
+        fr.sequence = seq
+        fr.gt = self.gt_of(seq) if self.gt_of is not None else None
+        return fr
+
     def loader(self, batch_size: int = 8, shuffle: bool = False, rng: Optional[np.random.Generator] = None,
                drop_last: bool = False, decode_threads: int = 0, decode_ahead: int = 2) -> Iterator[dict]:
         """Batches like ``DataLoader(dataset, batch_size, shuffle, collate_fn=collate_fn)`` (train_vit.py:76-79), already on the
@@ -204,7 +233,7 @@ class Av2BevDataset:
         inner = dataset_shim.BevBatchLoader(_LazySamples(self, order), batch_size, self.map_table,
                                             map_id_of=lambda s: s.map_index, is_train=self.is_train,
                                             num_sweeps=self.num_sweeps, drop_last=drop_last, sweep_store=self.store)
-        if decode_threads <= 0:
+        if decode_threads <= 0 or not self.columnar:
             return iter(inner)
         return self._prefetching(inner, order, batch_size, decode_threads, decode_ahead)
 
