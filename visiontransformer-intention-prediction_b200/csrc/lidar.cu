@@ -21,6 +21,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <vector>
 
 
 
@@ -687,26 +688,47 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
         const int rc = make_grid_tensor_map(&out_map, out, (uint64_t)B * S * kZ, kATW, kATH);
         if (rc) return rc;
     }
-    int next_slot = 0;
+    // slots of the per-(channel, output tile) bins, in class order; ONE re-binning launch for all resampled frames
+    std::vector<short> slot_of(B, (short)-1);
+    {
+        int next_slot = 0;
+        for (int cls = 1; cls < 4; ++cls)
+            for (int b = 0; b < B; ++b)
+                if (cls_of(b) == cls) slot_of[b] = (short)next_slot++;
+        AugTileFrames fl;
+        fl.n = 0;
+        auto flush_rebin = [&]() -> int {
+            if (fl.n == 0) return 0;
+            BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<<<dim3(kZ, S, fl.n), kRebinThreads, 0, st>>>(
+                              cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
+            fl.n = 0;
+            return 0;
+        };
+        for (int b = 0; b < B; ++b) {
+            if (cls_of(b) == 0) continue;
+            fl.src[fl.n] = fl.dst[fl.n] = (short)b;
+            fl.slot[fl.n] = slot_of[b];
+            if (++fl.n == 60) { const int rc = flush_rebin(); if (rc) return rc; }
+        }
+        const int rc = flush_rebin();
+        if (rc) return rc;
+    }
     for (int cls = 1; cls < 4; ++cls) {
         AugTileFrames fl;
         fl.n = 0;
         auto flush = [&]() -> int {
             if (fl.n == 0) return 0;
-            const dim3 rgrid(kZ, S, fl.n), grid(kATTiles, S, fl.n);
+            const dim3 grid(kATTiles, S, fl.n);
             switch (cls) {
                 case 1:
-                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, false><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, false><<<grid, kATThreads, AugTileCfg<true, false>::kSmem, st>>>(
                                       cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S, hints));
                     break;
                 case 2:
-                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<false, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<false, true><<<grid, kATThreads, AugTileCfg<false, true>::kSmem, st>>>(
                                       cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S, hints));
                     break;
                 default:
-                    BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<true, true><<<rgrid, kRebinThreads, 0, st>>>(cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, true><<<grid, kATThreads, AugTileCfg<true, true>::kSmem, st>>>(
                                       cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S, hints));
                     break;
@@ -717,7 +739,7 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
         for (int b = 0; b < B; ++b) {
             if (cls_of(b) != cls) continue;
             fl.src[fl.n] = fl.dst[fl.n] = (short)b;
-            fl.slot[fl.n] = (short)next_slot++;
+            fl.slot[fl.n] = slot_of[b];
             if (++fl.n == 60) { const int rc = flush(); if (rc) return rc; }
         }
         const int rc = flush();

@@ -176,8 +176,9 @@ __device__ __forceinline__ uint32_t rot_window_origin(int u, int v, const RotFwd
 }
 
 // ---- re-binning: row-band bins -> per-(channel, output tile) bins ---------------------------------------------------
-// grid (29 channels, S sweeps, frames of the class); record = (work-list entry of the source pixel for that tile, intensity bits)
-template <bool ROT, bool SCL>
+// grid (29 channels, S sweeps, resampled frames of ANY class: one launch per batch -- the kernel is one wave of latency-bound
+// CTAs, three per-class launches cost three such waves); record = (work-list entry of the source pixel for that tile,
+// intensity bits)
 __global__ void __launch_bounds__(kRebinThreads, 4) k_rebin_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
                                                           const uint32_t* __restrict__ ovf_cnt, const OvfRec* __restrict__ ovf,
                                                           const int32_t* __restrict__ sweep_off,
@@ -198,8 +199,11 @@ __global__ void __launch_bounds__(kRebinThreads, 4) k_rebin_aug(const uint32_t* 
     }
     if (tid == 0) s_over = 0;
     __syncthreads();
+    const bool ROT = P.do_rotate != 0, SCL = P.do_scale != 0;     // the frame's class (uniform per CTA)
     for (int t = tid; t < kATTiles; t += kRebinThreads) {
-        const AugTileGeo G = aug_tile_geo<ROT, SCL>(P, (t % kATBX) * kATW, (t / kATBX) * kATH);
+        const int tx0 = (t % kATBX) * kATW, ty0 = (t / kATBX) * kATH;
+        const AugTileGeo G = ROT ? (SCL ? aug_tile_geo<true, true>(P, tx0, ty0) : aug_tile_geo<true, false>(P, tx0, ty0))
+                                 : aug_tile_geo<false, true>(P, tx0, ty0);
         box[t] = make_int4(G.fx0, G.fy0, G.fx0 + G.FW - 1, G.fy0 + G.FH - 1);
         dorg[t] = make_short2((short)G.dx0, (short)G.dy0);
         hist[t] = 0;
