@@ -255,121 +255,121 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
     // binned completely, its CTAs walk the remaining chunks (normally this loop runs once).
 #pragma unroll 1
     for (uint32_t chunk0 = org + blockIdx.x * (uint32_t)kAggChunk; chunk0 < (uint32_t)end; chunk0 += gridDim.x * (uint32_t)kAggChunk) {
-    for (int i = tid; i < kTilesPerSweep; i += kAggThreads) hist[i] = 0;
-    __syncthreads();
-    // phase 1: records + per-tile rank inside the CTA (shared atomics)
-    auto emit = [&](int k, bool ok, const Voxel& v) {
-        uint32_t word = 0xFFFFFFFFu;
-        if (ok) {
-            const uint32_t band = (uint32_t)v.py / kFillRows;
-            const uint32_t bin = (uint32_t)v.zb * (kH / kFillRows) + band;
-            const uint32_t tcell = ((uint32_t)v.py - band * kFillRows) * kW + (uint32_t)v.px;
-            word = (bin << 13) | tcell;
-            rank[k] = (uint16_t)atomicAdd(&hist[bin], 1u);
-        }
-        recs[k] = make_uint2(word, v.bits);
-    };
-    if constexpr (MODE == 3) {
-        // 8 consecutive rows per thread and group: 56 B per thread in flight (4 vector loads), 2 x 512 threads per SM
+        for (int i = tid; i < kTilesPerSweep; i += kAggThreads) hist[i] = 0;
+        __syncthreads();
+        // phase 1: records + per-tile rank inside the CTA (shared atomics)
+        auto emit = [&](int k, bool ok, const Voxel& v) {
+            uint32_t word = 0xFFFFFFFFu;
+            if (ok) {
+                const uint32_t band = (uint32_t)v.py / kFillRows;
+                const uint32_t bin = (uint32_t)v.zb * (kH / kFillRows) + band;
+                const uint32_t tcell = ((uint32_t)v.py - band * kFillRows) * kW + (uint32_t)v.px;
+                word = (bin << 13) | tcell;
+                rank[k] = (uint16_t)atomicAdd(&hist[bin], 1u);
+            }
+            recs[k] = make_uint2(word, v.bits);
+        };
+        if constexpr (MODE == 3) {
+            // 8 consecutive rows per thread and group: 56 B per thread in flight (4 vector loads), 2 x 512 threads per SM
 #pragma unroll 1
-        for (int g = 0; g < kAggItems / 8; ++g) {
-            const uint32_t i8 = chunk0 + (uint32_t)((g * kAggThreads + tid) * 8);
-            const ColGroup grp = load_cols(in, i8, i8 < (uint32_t)end);
+            for (int g = 0; g < kAggItems / 8; ++g) {
+                const uint32_t i8 = chunk0 + (uint32_t)((g * kAggThreads + tid) * 8);
+                const ColGroup grp = load_cols(in, i8, i8 < (uint32_t)end);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t i = i8 + (uint32_t)u;
-                Voxel v;
-                v.bits = 0;
-                const bool ok = i >= (uint32_t)beg && i < (uint32_t)end && point_voxel<0>(col_point(grp, u), sT, flip, sRect, nrect, v);
-                emit((g * 8 + u) * kAggThreads + tid, ok, v);       // slot index: conflict-free, any bijection works
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t i = i8 + (uint32_t)u;
+                    Voxel v;
+                    v.bits = 0;
+                    const bool ok = i >= (uint32_t)beg && i < (uint32_t)end && point_voxel<0>(col_point(grp, u), sT, flip, sRect, nrect, v);
+                    emit((g * 8 + u) * kAggThreads + tid, ok, v);       // slot index: conflict-free, any bijection works
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int g = 0; g < kAggItems; g += 4) {
+                RawPoint<MODE> raw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = chunk0 + (uint32_t)((g + u) * kAggThreads + tid);      // < 2^32: n_points < 2^31, chunk < 2^13
+                    raw[u] = load_point<MODE>(in, (long long)i, i < (uint32_t)end);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = (g + u) * kAggThreads + tid;
+                    const uint32_t i = chunk0 + (uint32_t)k;
+                    Voxel v;
+                    v.bits = 0;
+                    const bool ok = (i < (uint32_t)end) && point_voxel<MODE>(raw[u], sT, flip, sRect, nrect, v);
+                    emit(k, ok, v);
+                }
             }
         }
-    } else {
+        __syncthreads();
+        // phase 2: one global claim per touched tile (all of a thread's claims are in flight together)
+        {
+            constexpr int kPer = (kTilesPerSweep + kAggThreads - 1) / kAggThreads;       // 3
+            uint32_t c[kPer], b0[kPer];
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int bin = tid + j * kAggThreads;
+                c[j] = bin < kTilesPerSweep ? hist[bin] : 0u;
+                b0[j] = 0u;
+                if (c[j]) b0[j] = atomicAdd(cnt + (size_t)bs * kTilesPerSweep + bin, c[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < kPer; ++j)
+                if (c[j]) base[tid + j * kAggThreads] = b0[j];
+        }
+        __syncthreads();
+        // phase 3: records to their slots; spills are ranked inside the CTA first (one shared atomic per warp) ...
+        if (tid == 0) s_spill_n = 0;
+        __syncthreads();
+        const int lane = tid & 31;
+        const uint32_t lt = (1u << lane) - 1u;
+        uint64_t hint_pol = 0;
+        if (l2_hints) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(hint_pol));   // small batches: see l2_hints_for()
 #pragma unroll 1
-    for (int g = 0; g < kAggItems; g += 4) {
-        RawPoint<MODE> raw[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t i = chunk0 + (uint32_t)((g + u) * kAggThreads + tid);      // < 2^32: n_points < 2^31, chunk < 2^13
-            raw[u] = load_point<MODE>(in, (long long)i, i < (uint32_t)end);
+        for (int it = 0; it < kAggItems; ++it) {
+            const int k = it * kAggThreads + tid;
+            const uint2 r = recs[k];
+            const bool ok = r.x != 0xFFFFFFFFu;
+            const uint32_t bin = r.x >> 13, tcell = r.x & 8191u;
+            const uint32_t tile = (uint32_t)bs * kTilesPerSweep + bin;
+            const uint32_t slot = ok ? base[bin] + rank[k] : 0u;
+            const bool spill = ok && slot >= (uint32_t)kBinCap;
+            if (ok && !spill) {
+                uint2* dst = bins + (size_t)tile * kBinCap + slot;
+                if (hint_pol) asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" :: "l"(dst), "r"(tcell), "r"(r.y), "l"(hint_pol) : "memory");
+                else *dst = make_uint2(tcell, r.y);
+            }
+            const uint32_t sp = __ballot_sync(0xFFFFFFFFu, spill);
+            uint32_t word = 0xFFFFFFFFu;                                 // not a spill
+            if (sp) {
+                uint32_t lbase = 0;
+                if (lane == __ffs(sp) - 1) lbase = atomicAdd(&s_spill_n, (uint32_t)__popc(sp));
+                lbase = __shfl_sync(0xFFFFFFFFu, lbase, __ffs(sp) - 1);
+                if (spill) { word = r.x; rank[k] = (uint16_t)(lbase + __popc(sp & lt)); }   // CTA-local overflow index (< 8192)
+            }
+            if (!spill) recs[k].x = 0xFFFFFFFFu;                         // only spills stay marked for phase 4
+            (void)word;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = (g + u) * kAggThreads + tid;
-            const uint32_t i = chunk0 + (uint32_t)k;
-            Voxel v;
-            v.bits = 0;
-            const bool ok = (i < (uint32_t)end) && point_voxel<MODE>(raw[u], sT, flip, sRect, nrect, v);
-            emit(k, ok, v);
-        }
-    }
-    }
-    __syncthreads();
-    // phase 2: one global claim per touched tile (all of a thread's claims are in flight together)
-    {
-        constexpr int kPer = (kTilesPerSweep + kAggThreads - 1) / kAggThreads;       // 3
-        uint32_t c[kPer], b0[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int bin = tid + j * kAggThreads;
-            c[j] = bin < kTilesPerSweep ? hist[bin] : 0u;
-            b0[j] = 0u;
-            if (c[j]) b0[j] = atomicAdd(cnt + (size_t)bs * kTilesPerSweep + bin, c[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < kPer; ++j)
-            if (c[j]) base[tid + j * kAggThreads] = b0[j];
-    }
-    __syncthreads();
-    // phase 3: records to their slots; spills are ranked inside the CTA first (one shared atomic per warp) ...
-    if (tid == 0) s_spill_n = 0;
-    __syncthreads();
-    const int lane = tid & 31;
-    const uint32_t lt = (1u << lane) - 1u;
-    uint64_t hint_pol = 0;
-    if (l2_hints) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(hint_pol));   // small batches: see l2_hints_for()
+        __syncthreads();
+        // ... phase 4: ONE global list-append atomic per CTA, then the spilled records go out
+        if (s_spill_n == 0) continue;                                    // uniform
+        // per-sweep lists: sweep bs owns ovf[sweep_off[bs] - sweep_off[0] ...) (a point spills at most once), count in ovf_cnt[bs]
+        if (tid == 0) s_spill_base = atomicAdd(ovf_cnt + bs, s_spill_n);
+        __syncthreads();
+        const uint32_t obase = (uint32_t)(in.sweep_off[bs] - in.sweep_off[0]) + s_spill_base;
 #pragma unroll 1
-    for (int it = 0; it < kAggItems; ++it) {
-        const int k = it * kAggThreads + tid;
-        const uint2 r = recs[k];
-        const bool ok = r.x != 0xFFFFFFFFu;
-        const uint32_t bin = r.x >> 13, tcell = r.x & 8191u;
-        const uint32_t tile = (uint32_t)bs * kTilesPerSweep + bin;
-        const uint32_t slot = ok ? base[bin] + rank[k] : 0u;
-        const bool spill = ok && slot >= (uint32_t)kBinCap;
-        if (ok && !spill) {
-            uint2* dst = bins + (size_t)tile * kBinCap + slot;
-            if (hint_pol) asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" :: "l"(dst), "r"(tcell), "r"(r.y), "l"(hint_pol) : "memory");
-            else *dst = make_uint2(tcell, r.y);
+        for (int it = 0; it < kAggItems; ++it) {
+            const int k = it * kAggThreads + tid;
+            const uint2 r = recs[k];
+            if (r.x == 0xFFFFFFFFu) continue;
+            OvfRec o;
+            o.idx = (unsigned long long)((uint32_t)bs * kTilesPerSweep + (r.x >> 13)) * kTileElems + (r.x & 8191u);
+            o.bits = r.y; o.pad = 0;
+            ovf[obase + rank[k]] = o;
         }
-        const uint32_t sp = __ballot_sync(0xFFFFFFFFu, spill);
-        uint32_t word = 0xFFFFFFFFu;                                 // not a spill
-        if (sp) {
-            uint32_t lbase = 0;
-            if (lane == __ffs(sp) - 1) lbase = atomicAdd(&s_spill_n, (uint32_t)__popc(sp));
-            lbase = __shfl_sync(0xFFFFFFFFu, lbase, __ffs(sp) - 1);
-            if (spill) { word = r.x; rank[k] = (uint16_t)(lbase + __popc(sp & lt)); }   // CTA-local overflow index (< 8192)
-        }
-        if (!spill) recs[k].x = 0xFFFFFFFFu;                         // only spills stay marked for phase 4
-        (void)word;
-    }
-    __syncthreads();
-    // ... phase 4: ONE global list-append atomic per CTA, then the spilled records go out
-    if (s_spill_n == 0) continue;                                    // uniform
-    // per-sweep lists: sweep bs owns ovf[sweep_off[bs] - sweep_off[0] ...) (a point spills at most once), count in ovf_cnt[bs]
-    if (tid == 0) s_spill_base = atomicAdd(ovf_cnt + bs, s_spill_n);
-    __syncthreads();
-    const uint32_t obase = (uint32_t)(in.sweep_off[bs] - in.sweep_off[0]) + s_spill_base;
-#pragma unroll 1
-    for (int it = 0; it < kAggItems; ++it) {
-        const int k = it * kAggThreads + tid;
-        const uint2 r = recs[k];
-        if (r.x == 0xFFFFFFFFu) continue;
-        OvfRec o;
-        o.idx = (unsigned long long)((uint32_t)bs * kTilesPerSweep + (r.x >> 13)) * kTileElems + (r.x & 8191u);
-        o.bits = r.y; o.pad = 0;
-        ovf[obase + rank[k]] = o;
-    }
     }   // chunk loop
 }
 
@@ -458,47 +458,47 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter_atomic(LidarIn in, uint
     const uint32_t org = MODE == 3 ? ((uint32_t)beg & ~7u) : (uint32_t)beg;
 #pragma unroll 1
     for (uint32_t chunk0 = org + blockIdx.x * (uint32_t)kBinChunk; chunk0 < (uint32_t)end; chunk0 += gridDim.x * (uint32_t)kBinChunk) {
-    uint32_t* addr[kBinItems];
-    uint32_t val[kBinItems];
-    if constexpr (MODE == 3) {
-        static_assert(kBinItems == 4, "two threads share one 8-row column group");
-        // thread t takes rows [4t, 4t+4) of the chunk: the 16 B / 8 B vectors are fetched by the pair of threads that share
-        // them (the second fetch hits L1), which keeps the chunk geometry of the row formats
-        const uint32_t i8 = chunk0 + (uint32_t)(threadIdx.x >> 1) * 8u;
-        const ColGroup grp = load_cols(in, i8, i8 < (uint32_t)end);
-        const int h = (threadIdx.x & 1) * 4;
+        uint32_t* addr[kBinItems];
+        uint32_t val[kBinItems];
+        if constexpr (MODE == 3) {
+            static_assert(kBinItems == 4, "two threads share one 8-row column group");
+            // thread t takes rows [4t, 4t+4) of the chunk: the 16 B / 8 B vectors are fetched by the pair of threads that share
+            // them (the second fetch hits L1), which keeps the chunk geometry of the row formats
+            const uint32_t i8 = chunk0 + (uint32_t)(threadIdx.x >> 1) * 8u;
+            const ColGroup grp = load_cols(in, i8, i8 < (uint32_t)end);
+            const int h = (threadIdx.x & 1) * 4;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const uint32_t i = i8 + (uint32_t)(h + it);
-            Voxel v;
-            addr[it] = nullptr; val[it] = 0;
-            const RawPoint<0> rp = h ? col_point(grp, 4 + it) : col_point(grp, it);
-            if (i >= (uint32_t)beg && i < (uint32_t)end && point_voxel<0>(rp, sT, flip, sRect, nrect, v)) {
-                addr[it] = out + ((size_t)(bs * kZ + v.zb) * kH + v.py) * kW + v.px;
-                val[it] = v.bits;
+            for (int it = 0; it < 4; ++it) {
+                const uint32_t i = i8 + (uint32_t)(h + it);
+                Voxel v;
+                addr[it] = nullptr; val[it] = 0;
+                const RawPoint<0> rp = h ? col_point(grp, 4 + it) : col_point(grp, it);
+                if (i >= (uint32_t)beg && i < (uint32_t)end && point_voxel<0>(rp, sT, flip, sRect, nrect, v)) {
+                    addr[it] = out + ((size_t)(bs * kZ + v.zb) * kH + v.py) * kW + v.px;
+                    val[it] = v.bits;
+                }
+            }
+        } else {
+            RawPoint<MODE> raw[kBinItems];
+#pragma unroll
+            for (int it = 0; it < kBinItems; ++it) {
+                const uint32_t i = chunk0 + (uint32_t)(it * kBinThreads + threadIdx.x);
+                raw[it] = load_point<MODE>(in, (long long)i, i < (uint32_t)end);
+            }
+#pragma unroll
+            for (int it = 0; it < kBinItems; ++it) {
+                const uint32_t i = chunk0 + (uint32_t)(it * kBinThreads + threadIdx.x);
+                Voxel v;
+                addr[it] = nullptr; val[it] = 0;
+                if (i < (uint32_t)end && point_voxel<MODE>(raw[it], sT, flip, sRect, nrect, v)) {
+                    addr[it] = out + ((size_t)(bs * kZ + v.zb) * kH + v.py) * kW + v.px;
+                    val[it] = v.bits;
+                }
             }
         }
-    } else {
-    RawPoint<MODE> raw[kBinItems];
 #pragma unroll
-    for (int it = 0; it < kBinItems; ++it) {
-        const uint32_t i = chunk0 + (uint32_t)(it * kBinThreads + threadIdx.x);
-        raw[it] = load_point<MODE>(in, (long long)i, i < (uint32_t)end);
-    }
-#pragma unroll
-    for (int it = 0; it < kBinItems; ++it) {
-        const uint32_t i = chunk0 + (uint32_t)(it * kBinThreads + threadIdx.x);
-        Voxel v;
-        addr[it] = nullptr; val[it] = 0;
-        if (i < (uint32_t)end && point_voxel<MODE>(raw[it], sT, flip, sRect, nrect, v)) {
-            addr[it] = out + ((size_t)(bs * kZ + v.zb) * kH + v.py) * kW + v.px;
-            val[it] = v.bits;
-        }
-    }
-    }
-#pragma unroll
-    for (int it = 0; it < kBinItems; ++it)
-        if (addr[it]) atomicMax(addr[it], val[it]);
+        for (int it = 0; it < kBinItems; ++it)
+            if (addr[it]) atomicMax(addr[it], val[it]);
     }   // chunk loop
 }
 
