@@ -67,3 +67,27 @@ def test_oracle_reproduces_the_reference_datasets_items():
         boxes, intents = z[f"eval{i}_boxes"].copy(), z[f"eval{i}_intents"].copy()
         bg.augment.apply_gt(p, boxes, intents)
         assert np.array_equal(boxes.astype(np.float32), z[f"train{i}_boxes"]) and np.array_equal(intents, z[f"train{i}_intents"])
+
+
+def test_annotation_gt_mirrors_prepare_gt_for_frame():
+    """AnnotationGT = utils.py:184-225 on annotations_with_intent.feather.  strict_reference reproduces what the reference
+    returned in this container (the golden); the default converts the quaternion to float64 first, as the reference's pinned
+    scipy would, and yields the filtered rows' boxes"""
+    import pandas as pd
+    from scipy.spatial.transform import Rotation as R
+    import bevgen_b200 as bg
+    z = load("dataset_items.npz")
+    seqs = bg.av2_dataset.make_sequences(bg.av2_dataset.find_scenarios(ROOT))
+    strict, dflt = bg.av2_dataset.AnnotationGT(strict_reference=True), bg.av2_dataset.AnnotationGT()
+    ann = pd.read_feather(ROOT / "minilog0000" / "annotations_with_intent.feather")
+    for i, s in enumerate(seqs):
+        g = strict(s)
+        assert np.array_equal(g["boxes_xywha"], z[f"eval{i}_boxes"]) and np.array_equal(g["intentions"], z[f"eval{i}_intents"])
+        d = dflt(s)
+        rows = ann[(ann["timestamp_ns"] == s["current_ts_ns"]) & ann["category"].isin(bg.constants.VEHICLE_CATEGORIES) & (ann["heuristic_intent"] != -1)]
+        assert len(rows) > 0 and d["boxes_xywha"].shape == (len(rows), 5) and d["boxes_xywha"].dtype == np.float32
+        assert d["intentions"].tolist() == rows["heuristic_intent"].astype(int).tolist() and d["intentions"].dtype == np.int64
+        q = rows[["qx", "qy", "qz", "qw"]].to_numpy(np.float64)
+        want = np.stack([rows["tx_m"], rows["ty_m"], rows["width_m"].abs(), rows["length_m"].abs(), R.from_quat(q).as_euler("xyz")[:, 2]], 1)
+        assert np.array_equal(d["boxes_xywha"], want.astype(np.float32))
+    assert dflt({"log_id": "none", "log_dir": str(ROOT / "nope"), "current_ts_ns": 0})["boxes_xywha"].shape == (0, 5)

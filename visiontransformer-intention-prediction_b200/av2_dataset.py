@@ -9,8 +9,9 @@ What is mirrored from the reference (so that the SAME directory yields the SAME 
     (``_create_sequences``, dataset.py:174-211)
   * per sample: pose lookup, which sweeps count as missing, ``None`` samples (``__getitem__``, dataset.py:285-345; here
     ``sweep_io.load_frame``)
-What is NOT here: ground truth (``prepare_gt_for_frame``, utils.py:184-225, stays the reference's host code -- pass
-``gt_of(sequence) -> {"boxes_xywha", "intentions"}``), and everything after the batch (models, loss).
+Ground truth: ``gt_of(sequence) -> {"boxes_xywha", "intentions"}``; the default, ``AnnotationGT``, is the host-side
+mirror of ``prepare_gt_for_frame`` (utils.py:184-225) on the log's ``annotations_with_intent.feather`` (a handful of boxes
+per frame; pandas / scipy exactly as the reference).  What is NOT here: everything after the batch (models, loss).
 
 Sweeps are decoded as AV2 stores them (float16 x,y,z + uint8 intensity columns) and uploaded ONCE into a device-resident
 ``SweepStore``; every sample that names a sweep reads it there (the windows share 9 of their 10 sweeps).
@@ -24,7 +25,7 @@ from typing import Callable, Iterator, List, Optional
 import numpy as np
 
 from . import bev_ops, dataset_shim, map_ops, maps, pose, sweep_io, sweep_store
-from .constants import LIDAR_SWEEPS
+from .constants import LIDAR_SWEEPS, VEHICLE_CATEGORIES
 
 
 def find_scenarios(data_dir, min_file_bytes: int = 1024) -> List[dict]:
@@ -67,6 +68,57 @@ def make_sequences(scenarios: List[dict], num_sweeps: int = LIDAR_SWEEPS) -> Lis
     return seqs
 
 
+class AnnotationGT:
+    """``gt_of`` callback: utils.py:184-225 (``prepare_gt_for_frame``) on ``<log>/annotations_with_intent.feather``
+    (dataset.py:220-233) -- rows of the sample's timestamp whose category is a vehicle category and whose precomputed
+    ``heuristic_intent`` is not -1 -> boxes ``[tx_m, ty_m, |width_m|, |length_m|, yaw]`` float32 (yaw =
+    ``R.from_quat([qx,qy,qz,qw]).as_euler('xyz')[2]``) and intention ids int64, in file order; rows scipy rejects are
+    skipped.  A log without the file yields no ground truth (the reference returns ``None`` for its samples).
+
+    Library-version caveat: the reference hands scipy the OBJECT-dtype slice ``box_row[['qx','qy','qz','qw']].values``
+    (utils.py:209).  scipy 1.13.1 (the reference's pin) converts it; scipy >= 1.14 raises ``ValueError`` ("Buffer dtype
+    mismatch"), which the reference's own ``except (ValueError, KeyError)`` swallows -- so on a current scipy the
+    reference silently drops EVERY box.  The default here converts the quaternion to float64 first (the pinned
+    environment's behaviour); ``strict_reference=True`` makes the literal call and reproduces whatever the installed
+    scipy does (this is what the dataset-level golden, generated in this container, contains)."""
+
+    def __init__(self, strict_reference: bool = False) -> None:
+        self._frames = {}
+        self.strict_reference = strict_reference
+
+    def __call__(self, seq: dict) -> Optional[dict]:
+        from scipy.spatial.transform import Rotation as R
+        df = self._frames.get(seq["log_id"], False)
+        if df is False:
+            path = Path(seq["log_dir"]) / "annotations_with_intent.feather"
+            df = None
+            if path.is_file():
+                import pandas as pd
+                df = pd.read_feather(path)
+                if "heuristic_intent" not in df.columns:
+                    df = None
+            self._frames[seq["log_id"]] = df
+        empty = {"boxes_xywha": np.zeros((0, 5), np.float32), "intentions": np.zeros((0,), np.int64)}
+        if df is None:
+            return empty
+        rows = df[(df["timestamp_ns"] == seq["current_ts_ns"]) & (df["category"].isin(VEHICLE_CATEGORIES)) &
+                  (df["heuristic_intent"] != -1)]
+        boxes, intents = [], []
+        for _, r in rows.iterrows():
+            try:
+                quat = r[["qx", "qy", "qz", "qw"]].values
+                if not self.strict_reference:
+                    quat = np.asarray(quat, dtype=np.float64)
+                yaw = R.from_quat(quat).as_euler("xyz", degrees=False)[2]
+                boxes.append([r["tx_m"], r["ty_m"], abs(r["width_m"]), abs(r["length_m"]), yaw])
+                intents.append(int(r["heuristic_intent"]))
+            except (ValueError, KeyError):
+                continue
+        if not boxes:
+            return empty
+        return {"boxes_xywha": np.asarray(boxes, np.float32), "intentions": np.asarray(intents, np.int64)}
+
+
 class _Sample:
     """what Av2BevDataset hands to BevBatchLoader: ``store_frame`` (sweeps named in the store), ``map_index``, ``gt``"""
     store_frame = None
@@ -92,7 +144,8 @@ class _LazySamples:
 class Av2BevDataset:
     def __init__(self, data_dir, num_sweeps: int = LIDAR_SWEEPS, is_train: bool = False,
                  gt_of: Optional[Callable[[dict], dict]] = None, store_points: int = 64_000_000, device=None) -> None:
-        self.num_sweeps, self.is_train, self.gt_of = int(num_sweeps), is_train, gt_of
+        self.num_sweeps, self.is_train = int(num_sweeps), is_train
+        self.gt_of = gt_of if gt_of is not None else AnnotationGT()
         self.scenarios = find_scenarios(data_dir)
         if not self.scenarios:
             raise ValueError(f"No valid scenarios found in {data_dir}. Please check the path and data integrity.")   # dataset.py:166

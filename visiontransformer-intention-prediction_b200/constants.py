@@ -19,5 +19,11 @@ INTENTIONS_MAP = {
     "RIGHT_CHANGE_LANE": 4, "STOPPING_STOPPED": 5, "PARKED": 6, "OTHER": 7,
 }
 
+# annotation categories kept as ground truth (constants.py:80-84; used by the Dataset mirror's default GT, utils.py:190-194)
+VEHICLE_CATEGORIES = {
+    "REGULAR_VEHICLE", "LARGE_VEHICLE", "BUS", "BOX_TRUCK", "TRUCK", "MOTORCYCLE", "SCHOOL_BUS", "ARTICULATED_BUS",
+    "VEHICULAR_TRAILER", "TRUCK_CAB", "BICYCLE", "BICYCLIST", "MOTORCYCLIST",
+}
+
 LIDAR_FRAME_BYTES = LIDAR_TOTAL_CHANNELS * GRID_HEIGHT_PX * GRID_WIDTH_PX * 4   # 334 080 000
 MAP_FRAME_BYTES = MAP_CHANNELS * GRID_HEIGHT_PX * GRID_WIDTH_PX * 4             # 10 368 000
