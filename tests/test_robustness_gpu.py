@@ -157,3 +157,27 @@ def test_algo_auto_switches_on_dense_scenes_and_back(bg, co):
     aug = [bg.AugParams(angle_deg=4.0), bg.AugParams()]
     ga = gen.generate(bd, aug, with_map=False)["lidar_bev"].cpu().numpy()
     assert np.array_equal(ga[0], co.rotate(wd[0], 4.0)) and np.array_equal(ga[1], wd[1])
+
+
+def test_large_batch_addresses_beyond_4gib(bg, co):
+    """128 frames = 42.8 GB of output: tile / plane / overflow indices must be 64-bit clean (frame 127 starts 42 GB in);
+    checked on the first, a middle and the last frame, plain and fused-augmented"""
+    S, B = 10, 128
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * 2 ** 30:
+        pytest.skip("needs ~90 GB of free device memory")
+    base = [bg.synthetic.quantize_f16(bg.synthetic.frame_c2(900 + i, n=1_500)) for i in range(3)]
+    frames = [base[i % 3] for i in range(B)]
+    want = [co.lidar_bev_fused(f.points4, f.sweep_offsets, f.rel_tf, S) for f in base]
+    batch = bg.FrameBatch.pack(frames, S, points_dtype="av2")
+    for algo in (bg.ALGO_TILED, bg.ALGO_ATOMIC):
+        out = bg.BevGenerator(algo=algo).generate(batch, with_map=False)["lidar_bev"]
+        for b in (0, 64, 127):
+            assert np.array_equal(out[b].cpu().numpy(), want[b % 3]), (algo, b)
+        del out
+    aug = [bg.AugParams(angle_deg=5.0) if b % 2 else bg.AugParams(flip=True) for b in range(B)]
+    out = bg.BevGenerator().generate(batch, aug, with_map=False)["lidar_bev"]
+    assert np.array_equal(out[127].cpu().numpy(), co.rotate(want[127 % 3], 5.0))
+    assert np.array_equal(out[126].cpu().numpy(), co.flip_w(want[126 % 3]))
+    del out
+    torch.cuda.empty_cache()
