@@ -76,7 +76,7 @@ class AnnotationGT:
     skipped.  A log without the file yields no ground truth (the reference returns ``None`` for its samples).
 
     Library-version caveat: the reference hands scipy the OBJECT-dtype slice ``box_row[['qx','qy','qz','qw']].values``
-    (utils.py:209).  scipy 1.13.1 (the reference's pin) converts it; scipy >= 1.14 raises ``ValueError`` ("Buffer dtype
+    (utils.py:208).  scipy 1.13.1 (the reference's pin) converts it; scipy >= 1.14 raises ``ValueError`` ("Buffer dtype
     mismatch"), which the reference's own ``except (ValueError, KeyError)`` swallows -- so on a current scipy the
     reference silently drops EVERY box.  The default here converts the quaternion to float64 first (the pinned
     environment's behaviour); ``strict_reference=True`` makes the literal call and reproduces whatever the installed
