@@ -115,14 +115,14 @@ __device__ __forceinline__ bool lidar_voxel(double x, double y, double z, int& p
     const double dx = __dsub_rn(tx, (double)ix), dy = __dsub_rn(ty, (double)iy), dz = __dsub_rn(tz, (double)iz);
     // written positively so that NaN / saturated values fall through to the literal path
     const bool safe = dx >= kEps && dx <= 1.0 - kEps && dy >= kEps && dy <= 1.0 - kEps && dz >= kEps && dz <= 1.0 - kEps;
-    int packed;
-    if (safe) {
-        packed = ((unsigned)ix < (unsigned)kW && (unsigned)iy < (unsigned)kH) ? ((min(iz, kZ - 1) << 20) | (iy << 10) | ix) : -1;
-    } else {
-        // near a cell boundary (or non-finite): quick reject far outside the grid, else evaluate literally
-        if (!(tx > -0.5 && tx < (double)kW + 0.5 && ty > -0.5 && ty < (double)kH + 0.5)) return false;
-        packed = lidar_voxel_exact(x, y, z);
+    if (safe) {                                                          // the common path: no packing round trip
+        if ((unsigned)ix >= (unsigned)kW || (unsigned)iy >= (unsigned)kH) return false;
+        px = ix; py = iy; zb = min(iz, kZ - 1);
+        return true;
     }
+    // near a cell boundary (or non-finite): quick reject far outside the grid, else evaluate literally
+    if (!(tx > -0.5 && tx < (double)kW + 0.5 && ty > -0.5 && ty < (double)kH + 0.5)) return false;
+    const int packed = lidar_voxel_exact(x, y, z);
     if (packed < 0) return false;
     px = packed & 1023; py = (packed >> 10) & 1023; zb = packed >> 20;
     return true;
