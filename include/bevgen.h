@@ -27,7 +27,9 @@
 extern "C" {
 #endif
 
-#define BEVGEN_ABI_VERSION 1
+/* 2: column (AV2) and sweep-store entry points, bevgen_store_put_cols, bevgen_lidar_overflow_total added; max_sweep_points is a
+ *    sizing hint and device-resident sweep offsets are clamped (round 2).  Everything declared in version 1 is unchanged. */
+#define BEVGEN_ABI_VERSION 2
 
 /* grid constants (reference constants.py:28-47) */
 #define BEVGEN_GRID_H 400

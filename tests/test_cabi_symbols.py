@@ -16,7 +16,7 @@ def test_header_symbols_exported():
     assert declared == set(_native.PROTOTYPES), declared ^ set(_native.PROTOTYPES)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.bevgen_abi_version() == 1
+    assert L.bevgen_abi_version() == 2
     assert L.bevgen_error_string(-2).decode().startswith("bevgen")
     assert L.bevgen_lidar_workspace_bytes(1000, 1, 10) > 16_000
 

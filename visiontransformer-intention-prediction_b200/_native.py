@@ -99,7 +99,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(L, name)          # AttributeError here = header / library mismatch
         fn.restype, fn.argtypes = res, args
-    if L.bevgen_abi_version() != 1:
+    if L.bevgen_abi_version() != 2:
         raise RuntimeError("libbevgen_b200.so ABI version mismatch")
     got = (C.c_double * 10)()
     L.bevgen_constants(got)
