@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
         const uint32_t lt = (1u << lane) - 1u;
         uint64_t hint_pol = 0;
         if (l2_hints) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(hint_pol));   // small batches: see l2_hints_for()
-#pragma unroll 1
+#pragma unroll 2
         for (int it = 0; it < kAggItems; ++it) {
             const int k = it * kAggThreads + tid;
             const uint2 r = recs[k];
@@ -343,15 +343,13 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
                 else *dst = make_uint2(tcell, r.y);
             }
             const uint32_t sp = __ballot_sync(0xFFFFFFFFu, spill);
-            uint32_t word = 0xFFFFFFFFu;                                 // not a spill
             if (sp) {
                 uint32_t lbase = 0;
                 if (lane == __ffs(sp) - 1) lbase = atomicAdd(&s_spill_n, (uint32_t)__popc(sp));
                 lbase = __shfl_sync(0xFFFFFFFFu, lbase, __ffs(sp) - 1);
-                if (spill) { word = r.x; rank[k] = (uint16_t)(lbase + __popc(sp & lt)); }   // CTA-local overflow index (< 8192)
+                // a spilled record keeps its CTA-local overflow index (< 8192) in `rank`, flagged by bit 15 for phase 4
+                if (spill) rank[k] = (uint16_t)(0x8000u | (lbase + __popc(sp & lt)));
             }
-            if (!spill) recs[k].x = 0xFFFFFFFFu;                         // only spills stay marked for phase 4
-            (void)word;
         }
         __syncthreads();
         // ... phase 4: ONE global list-append atomic per CTA, then the spilled records go out
@@ -364,11 +362,12 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
         for (int it = 0; it < kAggItems; ++it) {
             const int k = it * kAggThreads + tid;
             const uint2 r = recs[k];
-            if (r.x == 0xFFFFFFFFu) continue;
+            const uint32_t rk = rank[k];
+            if (r.x == 0xFFFFFFFFu || !(rk & 0x8000u)) continue;           // (ranks of valid records are < 8192: bit 15 = spilled)
             OvfRec o;
             o.idx = (unsigned long long)((uint32_t)bs * kTilesPerSweep + (r.x >> 13)) * kTileElems + (r.x & 8191u);
             o.bits = r.y; o.pad = 0;
-            ovf[obase + rank[k]] = o;
+            ovf[obase + (rk & 0x7FFFu)] = o;
         }
     }   // chunk loop
 }
