@@ -208,6 +208,17 @@ def test_sweep_store_ring_allocation_and_pins():
     assert put(4, 20) == 0 and 2 not in s._entries and not s._pins
     with pytest.raises(ValueError):
         s._alloc(72)
+    # the event an overwrite waits for: the epoch's own, the oldest kept one once it has been pruned, none if never read
+    s._events = {7: "e7", 9: "e9"}
+    assert s._wait_event(9) == "e9" and s._wait_event(3) == "e7" and s._wait_event(0) is None
+    # a batch whose sweeps have moved / gone since it was packed is refused
+    from bevgen_b200.sweep_store import StoreBatch
+    b = StoreBatch.__new__(StoreBatch)
+    b.rows = {k: s._entries[k] for k in s._entries}
+    s.check_resident(b)
+    b.rows = {2: (0, 20)}
+    with pytest.raises(KeyError):
+        s.check_resident(b)
 
 
 def test_sweep_store_ring_never_overlaps_live_sweeps():

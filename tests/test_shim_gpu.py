@@ -74,6 +74,56 @@ def test_install_rebinds_reference_style_module(bg):
     assert bev.shape == (290, 400, 720) and bev.any()
 
 
+def test_deferred_transform_equals_eager_path_and_oracle(bg):
+    """install()'s default: dataset.transform_points hands back DeferredPoints and create_intentnet_lidar_bev fuses the ten
+    transforms with the binning -- same grid as the eager float64 route and as the oracle, same skip rules and errors; the
+    array-like still reads as the transformed float64 array"""
+    from oracle import c_oracle as co
+    ds = types.ModuleType("dataset")
+    for n in ("transform_points", "create_intentnet_lidar_bev"):
+        setattr(ds, n, None)
+    assert "dataset.transform_points" in bg.dataset_shim.install(ds)
+    assert ds.transform_points is bg.bev_ops.transform_points_deferred
+    f = bg.synthetic.quantize_f16(bg.synthetic.frame_c2(3, n=4_000))
+    S = 10
+    raw = [f.sweep(s)[:, :3].astype(np.float16) for s in range(S)]           # what dataset.py:320 reads from the feather file
+    inten = [f.sweep(s)[:, 3].copy() for s in range(S)]
+    raw = [np.asfortranarray(r) if s % 2 else r for s, r in enumerate(raw)]   # pandas' .values is column-major; plain arrays are not
+    raw[6] = raw[6].astype(np.float32)
+    lazy = [ds.transform_points(raw[s], f.rel_tf[s]) for s in range(S)]
+    assert lazy[1].raw.flags.f_contiguous and lazy[0].raw.flags.c_contiguous and lazy[6].raw.dtype == np.float32
+    eager = [bg.transform_points(raw[s], f.rel_tf[s]) for s in range(S)]
+    assert all(isinstance(p, bg.bev_ops.DeferredPoints) and p.shape == e.shape and len(p) == len(e) and p.dtype == e.dtype
+               for p, e in zip(lazy, eager))
+    want = co.lidar_bev_fused(f.points4, f.sweep_offsets, f.rel_tf, S)
+    got = ds.create_intentnet_lidar_bev(lazy, inten)
+    assert got.dtype == np.float32 and got.shape == (290, 400, 720)
+    assert np.array_equal(got, want) and np.array_equal(got, bg.create_intentnet_lidar_bev(eager, inten))
+    assert all(p._value is None for p in lazy)                              # the fused route never materialised them
+    assert np.array_equal(np.asarray(lazy[2]), eager[2]) and np.array_equal(lazy[2][5:9], eager[2][5:9])
+    # missing sweeps, an empty one, fewer sweeps than expected (utils.py:71-76)
+    pl, il = list(lazy[:7]), list(inten[:7])
+    pl[1], il[1] = None, None
+    pl[4], il[4] = ds.transform_points(raw[4][:0], f.rel_tf[4]), inten[4][:0]
+    assert isinstance(pl[4], np.ndarray) and pl[4].shape == (0, 3)          # utils.py:29-30
+    pe = [None if p is None else np.asarray(p) for p in pl]
+    assert np.array_equal(ds.create_intentnet_lidar_bev(pl, il), bg.create_intentnet_lidar_bev(pe, il))
+    # a mix of deferred and plain arrays takes the eager route (still exact)
+    mixed = [eager[0]] + list(lazy[1:])
+    assert np.array_equal(ds.create_intentnet_lidar_bev(mixed, inten), want)
+    # float64 input is transformed right away; errors as the reference's
+    assert isinstance(ds.transform_points(raw[0].astype(np.float64), f.rel_tf[0]), np.ndarray)
+    with pytest.raises(IndexError):
+        ds.create_intentnet_lidar_bev(lazy, inten, 9)                       # utils.py:102
+    with pytest.raises(IndexError):
+        ds.create_intentnet_lidar_bev(lazy[:1], [inten[0][:-1]])
+    # the caller's array may change after the call: the deferred points keep their own copy
+    r0 = raw[0].copy()
+    p0 = ds.transform_points(r0, f.rel_tf[0])
+    r0[:] = 0
+    assert np.array_equal(np.asarray(p0), eager[0])
+
+
 def test_partitioned_augmentation_equals_in_order_path(bg):
     """resampled frames first (no identity copies) == the in-order path, up to the returned permutation"""
     md = bg.synthetic.synthetic_map(seed=3, rows=9, cols=9, n_cross=4)

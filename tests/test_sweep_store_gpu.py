@@ -126,6 +126,23 @@ def test_ring_eviction_and_wraparound(bg, co):
         store.put("too big", *(np.zeros(10**6, np.float16),) * 3, np.zeros(10**6, np.uint8))
 
 
+def test_batch_generated_again_after_eviction_is_an_error(bg, co):
+    """a packed batch is pinned until its first generate; a second generate of the same batch is fine while its sweeps are
+    still resident and a KeyError -- not a grid from other sweeps' points -- once an upload has taken their rows"""
+    S, n = 10, 2_000
+    sweeps, poses = bg.synthetic.sliding_log(30, n=n, seed=9)
+    store = bg.SweepStore(capacity_points=12 * n)
+    gen = bg.BevGenerator()
+    batch = bg.StoreBatch.pack(store, _store_frames(bg, store, sweeps, poses, [0]), S)
+    a = gen.generate(batch, with_map=False)["lidar_bev"].clone()
+    b = gen.generate(batch, with_map=False)["lidar_bev"]                # still resident: same bits
+    assert torch.equal(a, b)
+    _store_frames(bg, store, sweeps, poses, [12])                        # uploads sweeps 12..21: evicts 0..9
+    assert ("L", 0) not in store
+    with pytest.raises(KeyError):
+        gen.generate(batch, with_map=False)
+
+
 def test_batch_loader_with_store_equals_loader_without(bg):
     """BevBatchLoader(sweep_store=...): sliding-window samples that carry sweep_keys share their sweeps through the store;
     same batches (train-time augmentation included) as packing every sample's own ten sweeps"""

@@ -422,6 +422,112 @@ def transform_points(points: np.ndarray, transform_matrix: np.ndarray) -> np.nda
     return to_numpy_fresh(out)
 
 
+class DeferredPoints:
+    """What ``transform_points_deferred`` returns: a sweep's raw points and its matrix, standing in for the float64 ``(N,3)``
+    array ``transform_points`` would have returned.  ``create_intentnet_lidar_bev`` recognises it and runs transform +
+    binning as ONE fused pass over the raw points (what ``bevgen_lidar_bev_fused`` is for) instead of ten device round
+    trips of float64 arrays; anything else that touches it (``np.asarray``, indexing, arithmetic through ``__array__``)
+    gets the transformed array, computed on first use -- same bits either way."""
+
+    ndim = 2
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, raw: np.ndarray, T: np.ndarray) -> None:
+        self.raw, self.matrix, self._value = raw, T, None        # raw: float16 / float32 [N,3], own copy; matrix: float64 [4,4], own copy
+
+    @property
+    def shape(self):
+        return (self.raw.shape[0], 3)
+
+    def __len__(self) -> int:
+        return self.raw.shape[0]
+
+    def materialize(self) -> np.ndarray:
+        if self._value is None:
+            self._value = transform_points(self.raw, self.matrix)
+        return self._value
+
+    def __array__(self, dtype=None, copy=None):
+        v = self.materialize()
+        return v if dtype is None else v.astype(dtype, copy=False)
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+
+def transform_points_deferred(points: np.ndarray, transform_matrix: np.ndarray):
+    """``transform_points`` for the one place the reference calls it (dataset.py:340, whose results only feed
+    ``create_intentnet_lidar_bev`` at :347): float16 / float32 points -- what AV2's feather files hold, dataset.py:320 --
+    come back as a ``DeferredPoints``; every other input is transformed right away, exactly as ``transform_points``."""
+    points = np.asarray(points)
+    if points.ndim != 2 or points.shape[0] == 0 or points.shape[1] < 3 or points.dtype not in (np.float16, np.float32):
+        return transform_points(points, transform_matrix)
+    T = np.array(transform_matrix, dtype=np.float64)
+    if T.shape != (4, 4):
+        raise ValueError("transform_matrix must be 4x4")
+    raw = np.array(points[:, :3], order="K")                  # own copy, dtype and memory order kept (pandas' .values is column-major)
+    if not (raw.flags.c_contiguous or raw.flags.f_contiguous):
+        raw = np.ascontiguousarray(raw)
+    return DeferredPoints(raw, T)
+
+
+def _fused_from_deferred(points_list: Sequence, intensity_list: Sequence, num_expected_sweeps: int, algo: int) -> torch.Tensor:
+    """create_intentnet_lidar_bev when every loaded sweep is a DeferredPoints: the sweeps' raw coordinate and intensity
+    arrays are copied AS THEY ARE (contiguous memcpys) into one pinned staging buffer, uploaded once, laid out as (x, y, z,
+    intensity) float32 rows on the device (float16 -> float32 is exact), and transformed + binned by the fused launch.
+    Skip rules and errors as ``_pack_sweeps``."""
+    S = num_expected_sweeps
+    device = _require_cuda()
+    loaded = min(len(points_list), len(intensity_list))
+    counts = np.zeros(S, np.int64)
+    rel = np.tile(np.eye(4), (S, 1, 1))
+    parts, used = [], 0
+    for s in range(loaded):
+        pts, inten = points_list[s], intensity_list[s]
+        if pts is None or inten is None or pts.shape[0] == 0:
+            continue
+        if s >= S:
+            raise IndexError(f"index {s * LIDAR_HEIGHT_CHANNELS} is out of bounds for axis 0 with size {S * LIDAR_HEIGHT_CHANNELS}")
+        inten = np.asarray(inten)
+        if inten.shape[0] != pts.shape[0]:
+            raise IndexError("boolean index did not match: points and intensity lengths differ")
+        inten = np.ascontiguousarray(inten, dtype=np.float32).reshape(-1)       # utils.py:101: maximum.at into a float32 grid
+        counts[s], rel[s] = pts.shape[0], pts.matrix
+        a = used
+        b = a + (pts.raw.nbytes + 15) // 16 * 16
+        used = b + (inten.nbytes + 15) // 16 * 16
+        parts.append((pts.raw, inten, a, b))
+    off = np.zeros(S + 1, np.int32)
+    off[1:] = np.cumsum(counts)
+    total = int(off[-1])
+    nbytes = max(1, (used + (4 << 20) - 1) // (4 << 20)) * (4 << 20)            # few distinct sizes: the pool keys on them
+    stage = pinned_pool.take(nbytes)
+    try:
+        h = stage.numpy()
+        for raw, inten, a, b in parts:
+            flat = raw.reshape(-1, order="F" if raw.flags.f_contiguous and not raw.flags.c_contiguous else "C")
+            h[a:a + raw.nbytes] = flat.view(np.uint8)
+            h[b:b + inten.nbytes] = inten.view(np.uint8)
+        with torch.cuda.device(device):
+            d = stage[:used].to(device, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record()
+            rows = torch.empty((total, 4), dtype=torch.float32, device=device)
+            o = 0
+            for raw, inten, a, b in parts:
+                n = raw.shape[0]
+                src = d[a:a + raw.nbytes].view(torch.float16 if raw.dtype == np.float16 else torch.float32)
+                src = src.view(3, n).t() if raw.flags.f_contiguous and not raw.flags.c_contiguous else src.view(n, 3)
+                rows[o:o + n, :3].copy_(src)
+                rows[o:o + n, 3].copy_(d[b:b + 4 * n].view(torch.float32))
+                o += n
+            out = lidar_bev_from_sweeps(rows, off, rel.reshape(S, 16), 1, S, max_sweep_points=int(counts.max()) if S else 0, algo=algo)[0]
+            copied.synchronize()                                                # the staging buffer is free again (kernels keep running)
+    finally:
+        pinned_pool._release(stage)
+    return out
+
+
 def _pack_sweeps(points_list: Sequence, intensity_list: Sequence, num_expected_sweeps: int):
     """Concatenate the reference's list-of-arrays form into (points float64 [N,3], intensity float32 [N],
     offsets int32 [S+1]); applies the reference's skip rules (utils.py:71-76)."""
@@ -461,6 +567,10 @@ def create_intentnet_lidar_bev(points_list, intensity_list, num_expected_sweeps:
     Parity domain: float64 points (other dtypes are widened to float64 first), intensities
     finite or +inf and >= 0.
     """
-    pts, inten, off = _pack_sweeps(points_list, intensity_list, num_expected_sweeps)
-    out = lidar_bev_from_ego_points(pts, inten, off, 1, num_expected_sweeps, algo=algo)[0]
+    live = [p for p, i in zip(points_list, intensity_list) if p is not None and i is not None and p.shape[0] > 0]
+    if live and all(isinstance(p, DeferredPoints) for p in live):
+        out = _fused_from_deferred(points_list, intensity_list, num_expected_sweeps, algo)    # install() mode, dataset.py:340-347
+    else:
+        pts, inten, off = _pack_sweeps(points_list, intensity_list, num_expected_sweeps)
+        out = lidar_bev_from_ego_points(pts, inten, off, 1, num_expected_sweeps, algo=algo)[0]
     return out if as_tensor else to_numpy_fresh(out)

@@ -25,8 +25,13 @@ from . import bev_ops, map_ops, pipeline
 _REBOUND = ("transform_points", "create_intentnet_lidar_bev", "rasterize_map_ego_centric", "augment_bev")
 
 
-def install(dataset_module, utils_module=None) -> List[str]:
-    """Rebind the hot-path names inside the reference's ``dataset`` (and optionally ``utils``) module."""
+def install(dataset_module, utils_module=None, defer_transform: bool = True) -> List[str]:
+    """Rebind the hot-path names inside the reference's ``dataset`` (and optionally ``utils``) module.
+
+    ``defer_transform``: ``dataset.transform_points`` -- called only at dataset.py:340, its results only handed to
+    ``create_intentnet_lidar_bev`` at :347 -- returns ``bev_ops.DeferredPoints`` for float16 / float32 sweeps, so the ten
+    per-sweep transforms and the binning of a sample run as one fused launch over the raw points (same bits; the
+    array-like still turns into the float64 array for any other reader).  ``utils.transform_points`` stays eager."""
     impl = {"transform_points": bev_ops.transform_points,
             "create_intentnet_lidar_bev": bev_ops.create_intentnet_lidar_bev,
             "rasterize_map_ego_centric": map_ops.rasterize_map_ego_centric,
@@ -37,7 +42,10 @@ def install(dataset_module, utils_module=None) -> List[str]:
             continue
         for name in _REBOUND:
             if hasattr(mod, name):
-                setattr(mod, name, impl[name])
+                fn = impl[name]
+                if name == "transform_points" and defer_transform and mod is dataset_module:
+                    fn = bev_ops.transform_points_deferred
+                setattr(mod, name, fn)
                 done.append(f"{mod.__name__}.{name}")
         if mod is utils_module:
             for name, fn in (("random_flip_bev", _aug.random_flip_bev), ("random_rotate_bev", _aug.random_rotate_bev),

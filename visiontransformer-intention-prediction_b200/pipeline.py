@@ -242,8 +242,10 @@ class BevGenerator:
         ids = batch.map_ids
 
         store = getattr(batch, "store", None)
-        if store is not None and dev is not None:
-            store.ready(torch.cuda.current_stream(self.device))
+        if store is not None:
+            store.check_resident(batch)          # (a batch generated a second time after its sweeps were evicted: KeyError)
+            if dev is not None:
+                store.ready(torch.cuda.current_stream(self.device))
         d_start = dv.get("sweep_start")          # sweep store form: first store row per sweep
         skw = {} if d_start is None else {"total_points": batch.total_points}
 

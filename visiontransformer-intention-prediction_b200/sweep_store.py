@@ -141,7 +141,7 @@ class SweepStore:
                 raise ValueError("x, y, z, intensity must have the same length")
         row = self._alloc(max(8, _round8(n)))
         cap, base = self.capacity, self.columns.buf.data_ptr()
-        ev_used = self._events.get(self._wait_epoch)
+        ev_used = self._wait_event(self._wait_epoch)
         if ev_used is not None:
             self.copy_stream.wait_event(ev_used)                     # the last kernels that read the rows being overwritten
         # one call, four async copies on the store's copy stream (pageable sources are staged by the driver before it returns)
@@ -153,6 +153,25 @@ class SweepStore:
         self._entries[key] = (row, n)
         self.h2d_bytes += 7 * n
         return row, n
+
+    def _wait_event(self, epoch: int):
+        """event an upload over rows last read in ``epoch`` must wait for: that epoch's own, or -- when it has been pruned --
+        the oldest one still kept (recorded later, so waiting for it is merely conservative); ``None``: never read"""
+        if epoch <= 0:
+            return None
+        ev = self._events.get(epoch)
+        if ev is None and self._events:
+            ev = self._events[min(self._events)]
+        return ev
+
+    def check_resident(self, batch: "StoreBatch") -> None:
+        """KeyError unless every sweep ``batch`` names still sits where it was when the batch was packed.  A batch is
+        protected from eviction until its first ``generate``; generating it AGAIN is fine as long as no upload has taken its
+        rows in between -- this check turns that case into an error instead of a grid built from another sweep's points."""
+        for k, where in batch.rows.items():
+            if self._entries.get(k) != where:
+                raise KeyError(f"sweep {k!r} named by this batch is no longer resident in the store (evicted after the batch's "
+                               "first generate call); pack the batch again")
 
     def ready(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """``stream`` (default: current) waits for every upload issued so far."""
@@ -210,6 +229,7 @@ class StoreBatch:
     max_sweep_points: int
     total_points: int
     keys: tuple = ()                 # distinct sweeps named (pinned in the store until the batch is generated or dropped)
+    rows: dict = dataclasses.field(default_factory=dict)     # key -> (first row, points) at pack time (SweepStore.check_resident)
     _finalizer: object = None
 
     points_format = "av2-store"
@@ -263,7 +283,7 @@ class StoreBatch:
         ids = np.full(B, -1, np.int64) if map_ids is None else np.asarray(map_ids, np.int64)
         keys = tuple({k for f in frames for k in f.keys if k is not None})
         batch = StoreBatch(store, pin(start.reshape(-1)), pin(off.astype(np.int32)), pin(rel.reshape(B * S, 16)), pin(ego.reshape(B, 9)),
-                           ids, B, S, int(counts.max()) if B else 0, int(off[-1]), keys)
+                           ids, B, S, int(counts.max()) if B else 0, int(off[-1]), keys, {k: store.rows(k) for k in keys})
         store._pin(keys)
         batch._finalizer = weakref.finalize(batch, store._unpin, keys)
         return batch
