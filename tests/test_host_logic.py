@@ -203,7 +203,7 @@ def test_sweep_store_ring_allocation_and_pins():
     s._pin([2])
     with pytest.raises(RuntimeError):
         put(4, 20)                                                   # would overwrite pinned sweep 2
-    assert list(s._entries) == [2, 3]
+    assert list(s._entries) == [2, 3] and s._wait_epoch == 5        # (a failed allocation keeps the pending wait)
     s._unpin([2])
     assert put(4, 20) == 0 and 2 not in s._entries and not s._pins
     with pytest.raises(ValueError):

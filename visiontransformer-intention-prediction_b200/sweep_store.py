@@ -62,7 +62,7 @@ class SweepStore:
         self._events = {}                       # epoch -> event recorded by consumed()
         self._last_use = {}                     # key -> epoch of the last consumed batch that named it
         self._pins = collections.Counter()      # key -> packed batches that name it and have not been consumed yet
-        self._wait_epoch = 0                    # set by _alloc: newest epoch an evicted sweep was used in
+        self._wait_epoch = 0                    # newest epoch a sweep evicted since the last upload was used in
         self.h2d_bytes = 0                      # bytes uploaded since construction (bench accounting)
         self.evictions = 0
 
@@ -97,7 +97,8 @@ class SweepStore:
     def _alloc(self, need: int) -> int:
         if need > self.capacity:
             raise ValueError(f"sweep of {need} rows does not fit a store of {self.capacity}")
-        self._wait_epoch = 0
+        # (_wait_epoch accumulates over the evictions below and is cleared by put() once the wait has been issued: an
+        #  allocation that fails half-way -- pinned sweep -- leaves it set for the next one)
         if self._head + need > self.capacity:                       # wrap: the rows up to the end go first ...
             while self._entries and next(iter(self._entries.values()))[0] >= self._head:
                 self._evict_front()
@@ -144,6 +145,7 @@ class SweepStore:
         ev_used = self._wait_event(self._wait_epoch)
         if ev_used is not None:
             self.copy_stream.wait_event(ev_used)                     # the last kernels that read the rows being overwritten
+        self._wait_epoch = 0
         # one call, four async copies on the store's copy stream (pageable sources are staged by the driver before it returns)
         rc = _native.lib().bevgen_store_put_cols(base + 2 * row, base + 2 * (cap + row), base + 2 * (2 * cap + row), base + 6 * cap + row,
                                                  *ptrs, n, self.copy_stream.cuda_stream)
