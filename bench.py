@@ -150,6 +150,21 @@ def cpu_reference(workload: str, points: int, steps: int, warmup: int, workers: 
     return workers * len(step_times) / total, total / len(step_times), len(step_times)
 
 
+def cpu_single_process(workload: str, points: int, frames: int = 2, quantize: bool = False):
+    """frames/s of the CPU path as the reference itself runs it: ONE process (DataLoader num_workers=0, train_vit.py:20),
+    library-default threading (OpenBLAS / OpenCV pools) -- SURVEY.md 8(d)'s variant (i).  Best of `frames` frames."""
+    import tempfile
+    import bevgen_b200 as bg
+    map_path = None
+    if WORKLOADS[workload]["map"]:
+        map_path = os.path.join(tempfile.gettempdir(), f"bevgen_bench_map1_{os.getpid()}.json")
+        bg.synthetic.write_map_json(bg.synthetic.synthetic_map(), map_path)
+    best = min(_cpu_worker((workload, points, 900 + i, map_path, 1000 * 5 + 900 + i, quantize)) for i in range(frames))
+    if map_path:
+        os.unlink(map_path)
+    return 1.0 / best
+
+
 def host_threads() -> int:
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -166,6 +181,7 @@ def run_reference(args) -> None:
     fps, step_s, nsteps = cpu_reference(args.workload, args.points, args.steps, args.warmup, workers,
                                         quantize=args.points_dtype != "f32")
     pts_frame = wl.get("loaded_sweeps", 10) * args.points
+    single = cpu_single_process(args.workload, args.points, 2, quantize=args.points_dtype != "f32")
     line = {
         "impl": "reference", "metric": "bev_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": nsteps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -175,7 +191,10 @@ def run_reference(args) -> None:
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
                          "sample": f"{nsteps} steps x {workers} frames of the configured workload: the reference's numpy/OpenCV call "
                                    f"sequence (oracle/numpy_port.py), one frame per worker process per step, {workers} worker "
-                                   "processes with library-default threads each (the reference itself is single-process)"},
+                                   "processes with library-default threads each (the reference itself is single-process)",
+                         "single_process_value": single,
+                         "single_process_note": "the same call sequence in ONE process with library-default threading, as the "
+                                                "reference's own loader runs it (num_workers=0, train_vit.py:20); best of 2 frames"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -527,7 +546,10 @@ def run_ours(args) -> None:
                                         quantize=args.points_dtype != "f32")
         cpu = {"value": cfps, "unit": "frames/s", "cores": workers, "kind": "port",
                "sample": f"{cn} steps x {workers} frames of the same workload through oracle/numpy_port.py "
-                         f"({workers} worker processes, one frame each per step; {cstep:.2f} s/step)"}
+                         f"({workers} worker processes, one frame each per step; {cstep:.2f} s/step)",
+               "single_process_value": cpu_single_process(args.workload, args.points, 2, quantize=args.points_dtype != "f32"),
+               "single_process_note": "the same call sequence in ONE process with library-default threading, as the reference's "
+                                      "own loader runs it (num_workers=0, train_vit.py:20); best of 2 frames"}
 
     line = {
         "metric": "bev_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
