@@ -9,7 +9,7 @@ import bevgen_b200 as bg
 from bevgen_b200 import _native
 
 print("BEVGEN_L2_HINTS =", os.environ.get("BEVGEN_L2_HINTS", "(auto)"))
-for B in (1, 2, 4, 8, 16, 32):
+for B in [int(a) for a in sys.argv[1:]] or (1, 2, 4, 8, 16, 32):
     frames = [bg.synthetic.quantize_f16(bg.synthetic.frame_c2(i)) for i in range(2)]
     frames = [frames[i % 2] for i in range(B)]
     batch = bg.FrameBatch.pack(frames, 10, points_dtype="av2")

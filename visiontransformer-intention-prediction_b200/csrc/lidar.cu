@@ -217,6 +217,16 @@ constexpr int kBinCap = 128;                                         // records 
 constexpr int kTilesPerSweep = kFillPerSweep;                        // 1160
 constexpr int kTileElems = kFillRows * kW;                           // 7200 floats per tile
 struct OvfRec { unsigned long long idx; uint32_t bits; uint32_t pad; };
+// Row-band bin records: 8 bytes (cell inside the tile, intensity float bits) -- or 4 bytes where every intensity is a float
+// whose low 16 bits are zero, which holds for AV2's uint8 intensities (MODE 3: an integer 0..255 has at most 8 significant
+// bits): cell (13 bits) | upper half of the float (sign 0, exponent, 7 mantissa bits) << 13.  Same bins array, 4-byte stride;
+// half the record bytes written by k_bin_fixed and, what matters, read by k_tile_store in the middle of its write stream.
+template <int MODE> constexpr bool kRec4 = MODE == 3;
+__device__ __forceinline__ uint32_t band_rec_pack(uint32_t cell, uint32_t bits) { return cell | ((bits >> 16) << 13); }
+__device__ __forceinline__ uint2 band_rec_unpack(uint32_t w) { return make_uint2(w & 8191u, (w >> 13) << 16); }
+__device__ __forceinline__ uint2 band_rec_load(const uint2* __restrict__ bins, size_t idx, int rec4) {
+    return rec4 ? band_rec_unpack(__ldg(reinterpret_cast<const uint32_t*>(bins) + idx)) : __ldg(bins + idx);
+}
 
 // CTA-aggregated: a CTA takes AggCfg<ITEMS>::kChunk consecutive points of one sweep, ranks its records per tile with SHARED
 // atomics, then claims each touched tile's slots with ONE global atomic (instead of one per record) and writes
@@ -338,9 +348,16 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
             const uint32_t slot = ok ? base[bin] + rank[k] : 0u;
             const bool spill = ok && slot >= (uint32_t)kBinCap;
             if (ok && !spill) {
-                uint2* dst = bins + (size_t)tile * kBinCap + slot;
-                if (hint_pol) asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" :: "l"(dst), "r"(tcell), "r"(r.y), "l"(hint_pol) : "memory");
-                else *dst = make_uint2(tcell, r.y);
+                if (kRec4<MODE>) {                                       // AV2 intensities: 4-byte records (band_rec_pack)
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(bins) + (size_t)tile * kBinCap + slot;
+                    const uint32_t w = band_rec_pack(tcell, r.y);
+                    if (hint_pol) asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(dst), "r"(w), "l"(hint_pol) : "memory");
+                    else *dst = w;
+                } else {
+                    uint2* dst = bins + (size_t)tile * kBinCap + slot;
+                    if (hint_pol) asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" :: "l"(dst), "r"(tcell), "r"(r.y), "l"(hint_pol) : "memory");
+                    else *dst = make_uint2(tcell, r.y);
+                }
             }
             const uint32_t sp = __ballot_sync(0xFFFFFFFFu, spill);
             if (sp) {
@@ -373,7 +390,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) k_bin_fixed(LidarIn in, uint32
 }
 
 __global__ void __launch_bounds__(128) k_tile_store(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins,
-                                                    float* __restrict__ out, uint32_t t0, int l2_hints) {
+                                                    float* __restrict__ out, uint32_t t0, int l2_hints, int rec4) {
     extern __shared__ __align__(128) unsigned char ztile[];
     uint32_t* const tile = reinterpret_cast<uint32_t*>(ztile);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -385,7 +402,8 @@ __global__ void __launch_bounds__(128) k_tile_store(const uint32_t* __restrict__
     // the write stream than the dependent load costs in latency -- 7 resident CTAs per SM hide it)
     const bool have = (uint32_t)tid < n;
     uint2 rec = make_uint2(0xFFFFFFFFu, 0u);
-    if (have) rec = __ldcs(bins + t * kBinCap + tid);
+    if (have) rec = rec4 ? band_rec_unpack(__ldcs(reinterpret_cast<const uint32_t*>(bins) + t * kBinCap + tid))
+                         : __ldcs(bins + t * kBinCap + tid);
     __syncthreads();
     if (n) {                                                    // uniform
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, rec.x);      // dedupe equal cells inside the warp
@@ -539,11 +557,13 @@ int launch_bin(const LidarIn& in, int n_sweeps, int max_sweep_points, uint32_t* 
 // k_tile_store finds its records in L2 instead of reading HBM in the middle of its own write stream.  Pays only while the
 // bins of the whole launch fit in L2 next to the stream -- measured on B200, k_tile_store us/frame without -> with hints:
 // 2 frames 54.0 -> 48.2, 4: 51.9 -> 46.3, 8: 50.6 -> 46.7, 16: 49.8 -> 48.8, 32: 49.3 -> 49.9 (profiles/r2_exp_l2_hints.txt).
+// With 4-byte records (AV2 intensities) the bins are half as large and the hints pay up to 32 frames: 16: 48.5 -> 46.5,
+// 32: 47.8 -> 47.5, 40: 47.7 -> 47.7, 48: 47.7 -> 48.0 (profiles/r2_exp_rec4.txt).
 // BEVGEN_L2_HINTS=0/1 forces them off / on for measurements.
-int l2_hints_for(int sweeps_in_launch) {
+int l2_hints_for(int sweeps_in_launch, bool rec4) {
     static const int forced = [] { const char* e = getenv("BEVGEN_L2_HINTS"); return e ? atoi(e) : -1; }();
     if (forced >= 0) return forced != 0;
-    return sweeps_in_launch <= 160;
+    return sweeps_in_launch <= (rec4 ? 320 : 160);
 }
 
 // workspace of the tiled algorithm: [cnt u32 per tile | ovf_cnt] [bins: kBinCap records per tile] [overflow list]
@@ -605,7 +625,7 @@ int launch_lidar(LidarIn in, int B, int S, long long total_points, int max_sweep
         // one binning pass into fixed-capacity tile bins, one raster CTA per tile (smem tile + ONE TMA store), overflow REDs
         const TiledWorkspace L = tiled_layout(total_points, B, S);
         if (!workspace || workspace_bytes < L.bytes) return BEVGEN_E_WORKSPACE;
-        const int hints = l2_hints_for(B * S);
+        const int hints = l2_hints_for(B * S, kRec4<MODE>);
         char* wp = static_cast<char*>(workspace);
         uint32_t* cnt = reinterpret_cast<uint32_t*>(wp + L.cnt);
         uint32_t* ovf_cnt = cnt + ntiles;
@@ -618,7 +638,7 @@ int launch_lidar(LidarIn in, int B, int S, long long total_points, int max_sweep
             const int rc = launch_bin<MODE>(in, B * S, max_sweep_points, cnt, bins, ovf_cnt, ovf, hints, st);
             if (rc) return rc;
         }
-        BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<(unsigned)ntiles, 128, kFillBytes, st>>>(cnt, bins, out, 0u, hints));
+        BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<(unsigned)ntiles, 128, kFillBytes, st>>>(cnt, bins, out, 0u, hints, (int)kRec4<MODE>));
         if (chunks > 0)
             BEVGEN_LAUNCH("k_overflow_red", st, k_overflow_red<<<dim3(kOvfCtas, B * S), 256, 0, st>>>(
                               ovf_cnt, ovf, in.sweep_off, reinterpret_cast<uint32_t*>(out), nullptr, S));
@@ -650,7 +670,7 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
     }
     const TiledWorkspace L = tiled_layout(total_points, B, S, n_resampled);
     if (!workspace || workspace_bytes < L.bytes) return BEVGEN_E_WORKSPACE;
-    const int hints = l2_hints_for(B * S);
+    const int hints = l2_hints_for(B * S, kRec4<MODE>);
     char* wp = static_cast<char*>(workspace);
     uint32_t* cnt = reinterpret_cast<uint32_t*>(wp + L.cnt);
     uint32_t* ovf_cnt = cnt + ntiles;
@@ -675,7 +695,7 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
         int e = b;
         while (e < B && cls_of(e) == 0) ++e;
         const unsigned t0 = (unsigned)((size_t)b * S * kTilesPerSweep), nt = (unsigned)((size_t)(e - b) * S * kTilesPerSweep);
-        BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<nt, 128, kFillBytes, st>>>(cnt, bins, out, t0, hints));
+        BEVGEN_LAUNCH("k_tile_store", st, k_tile_store<<<nt, 128, kFillBytes, st>>>(cnt, bins, out, t0, hints, (int)kRec4<MODE>));
         any_plain = true;
         b = e;
     }
@@ -699,7 +719,7 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
         auto flush_rebin = [&]() -> int {
             if (fl.n == 0) return 0;
             BEVGEN_LAUNCH("k_rebin_aug", st, k_rebin_aug<<<dim3(kZ, S, fl.n), kRebinThreads, 0, st>>>(
-                              cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S));
+                              cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, in.aug, fl, S, (int)kRec4<MODE>));
             fl.n = 0;
             return 0;
         };
@@ -721,15 +741,15 @@ int launch_lidar_augmented(LidarIn in, int B, int S, long long total_points, int
             switch (cls) {
                 case 1:
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, false><<<grid, kATThreads, AugTileCfg<true, false>::kSmem, st>>>(
-                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S, hints));
+                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S, hints, (int)kRec4<MODE>));
                     break;
                 case 2:
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<false, true><<<grid, kATThreads, AugTileCfg<false, true>::kSmem, st>>>(
-                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S, hints));
+                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S, hints, (int)kRec4<MODE>));
                     break;
                 default:
                     BEVGEN_LAUNCH("k_tile_aug", st, k_tile_aug<true, true><<<grid, kATThreads, AugTileCfg<true, true>::kSmem, st>>>(
-                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S, hints));
+                                      cnt, bins, ovf_cnt, ovf, in.sweep_off, cnt2, bins2, out_map, in.aug, fl, S, hints, (int)kRec4<MODE>));
                     break;
             }
             fl.n = 0;

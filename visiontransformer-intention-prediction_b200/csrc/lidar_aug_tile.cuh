@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(kRebinThreads, 4) k_rebin_aug(const uint32_t* 
                                                           const uint32_t* __restrict__ ovf_cnt, const OvfRec* __restrict__ ovf,
                                                           const int32_t* __restrict__ sweep_off,
                                                           uint32_t* __restrict__ cnt2, uint2* __restrict__ bins2,
-                                                          const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S) {
+                                                          const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S,
+                                                          int rec4) {
     __shared__ bevgen_aug_params P;
     __shared__ int4 box[kATTiles];                           // footprint of each output tile: x0, y0, x1, y1 (inclusive)
     __shared__ short2 dorg[kATTiles];                        // origin of its rotation destination region
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kRebinThreads, 4) k_rebin_aug(const uint32_t* 
     for (int j = 0; j < kPerWarp; ++j) {
         if (nb[j] > (uint32_t)kBinCap) { if (lane == 0) s_over = 1; nb[j] = kBinCap; }
         first[j] = make_uint2(0u, 0u);
-        if ((uint32_t)lane < nb[j]) first[j] = __ldg(bins + (bin_base + warp + j * kWarps) * kBinCap + lane);
+        if ((uint32_t)lane < nb[j]) first[j] = band_rec_load(bins, (bin_base + warp + j * kWarps) * kBinCap + lane, rec4);
     }
     auto place = [&](int band, uint2 rec) {
         const int r = (int)(rec.x / (uint32_t)kW), u = (int)rec.x - r * kW, v = band * kFillRows + r;
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(kRebinThreads, 4) k_rebin_aug(const uint32_t* 
     for (int j = 0; j < kPerWarp; ++j) {
         const int band = warp + j * kWarps;
         if ((uint32_t)lane < nb[j]) place(band, first[j]);
-        for (uint32_t i = lane + 32; i < nb[j]; i += 32) place(band, __ldg(bins + (bin_base + band) * kBinCap + i));
+        for (uint32_t i = lane + 32; i < nb[j]; i += 32) place(band, band_rec_load(bins, (bin_base + band) * kBinCap + i, rec4));
     }
     __syncthreads();
     if (s_over) {
@@ -367,7 +368,7 @@ __device__ __forceinline__ void scl_row(int u, int v, int r, const AugTileGeo& G
 // -> max into T0.  Kept out of line so that its registers do not count against the common path.
 struct AugSlowArgs {                                         // parked in shared memory: only the slow path reads them
     const uint32_t* cnt; const uint2* bins; const uint32_t* ovf_cnt; const OvfRec* ovf; const int32_t* sweep_off;
-    int bs;
+    int bs, rec4;
 };
 static __device__ __noinline__ void at_slow_fill(const AugSlowArgs* a, int z, int fx0, int fy0, int FW, int FH, float* __restrict__ T0) {
     const uint32_t* __restrict__ cnt = a->cnt;
@@ -384,7 +385,7 @@ static __device__ __noinline__ void at_slow_fill(const AugSlowArgs* a, int z, in
         uint32_t nb = __ldg(cnt + t);
         if (nb > (uint32_t)kBinCap) { spilled = true; nb = kBinCap; }
         if ((uint32_t)tid < nb) {
-            const uint2 rec = __ldg(bins + t * kBinCap + tid);
+            const uint2 rec = band_rec_load(bins, t * kBinCap + tid, a->rec4);
             const int r = (int)(rec.x / (uint32_t)kW), fx = (int)rec.x - r * kW - fx0, fy = band * kFillRows + r - fy0;
             if ((unsigned)fx < (unsigned)FW && (unsigned)fy < (unsigned)FH)
                 atomicMax(reinterpret_cast<uint32_t*>(T0) + fy * FW + fx, rec.y);
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(kATThreads, AugTileCfg<ROT, SCL>::kMinBlocks)
 k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, const uint32_t* __restrict__ ovf_cnt,
            const OvfRec* __restrict__ ovf, const int32_t* __restrict__ sweep_off, const uint32_t* __restrict__ cnt2,
            const uint2* __restrict__ bins2, const __grid_constant__ CUtensorMap out_map,
-           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S, int l2_hints) {
+           const bevgen_aug_params* __restrict__ params, AugTileFrames fl, int S, int l2_hints, int rec4) {
     static_assert(ROT || SCL, "frames that neither rotate nor scale go through k_tile_store");
     using Cfg = AugTileCfg<ROT, SCL>;
     extern __shared__ __align__(128) unsigned char at_smem[];
@@ -470,7 +471,7 @@ k_tile_aug(const uint32_t* __restrict__ cnt, const uint2* __restrict__ bins, con
 
     // ---- geometry, once per CTA ---------------------------------------------------------------------------------
     if (tid == 0) {
-        SA.cnt = cnt; SA.bins = bins; SA.ovf_cnt = ovf_cnt; SA.ovf = ovf; SA.sweep_off = sweep_off; SA.bs = fsrc * S + sweep;
+        SA.cnt = cnt; SA.bins = bins; SA.ovf_cnt = ovf_cnt; SA.ovf = ovf; SA.sweep_off = sweep_off; SA.bs = fsrc * S + sweep; SA.rec4 = rec4;
         G = aug_tile_geo<ROT, SCL>(P, ox0, oy0);
         nW2 = 0;
     }
