@@ -243,3 +243,18 @@ def test_sweep_store_ring_never_overlaps_live_sweeps():
             assert k in s._entries
 
     run()
+
+
+def test_uint8_intensities_fit_the_four_byte_bin_record():
+    """csrc/lidar.cu band_rec_pack / band_rec_unpack: AV2 columns carry uint8 intensities; as float32 (dataset.py:321) every
+    one of them has its low 16 bits clear, so `cell | (bits >> 16) << 13` keeps cell (13 bits: 10 rows x 720 columns) and
+    intensity exactly, fits 32 bits, and orders like the float (the tile kernel takes the max of the unpacked bits)"""
+    v = np.arange(256, dtype=np.float32)
+    bits = v.view(np.uint32)
+    assert not (bits & 0xFFFF).any()
+    cell = np.uint32(10 * 720 - 1)
+    assert int(cell) < 1 << 13
+    w = cell | ((bits >> np.uint32(16)) << np.uint32(13))
+    assert int(w.astype(np.uint64).max()) < 1 << 32
+    assert np.array_equal(w & np.uint32(8191), np.full(256, cell)) and np.array_equal((w >> np.uint32(13)) << np.uint32(16), bits)
+    assert (np.diff(bits.astype(np.int64)) > 0).all()                # unsigned order of the bits == order of the values
