@@ -153,18 +153,19 @@ class BevGenerator:
         """Async H2D of the packed batch (pinned -> device) on the current stream.  A ``sweep_store.StoreBatch`` uploads only
         its per-frame tables: the points are the store's resident columns (the stream waits for the store's uploads)."""
         d = self.device
-        dv = {"sweep_offsets": batch.sweep_offsets.to(d, non_blocking=True),
-              "rel_tf": batch.rel_tf.to(d, non_blocking=True), "ego_T": batch.ego_T.to(d, non_blocking=True)}
         store = getattr(batch, "store", None)
         if store is not None:
             if store.device != d:
                 raise ValueError(f"sweep store lives on {store.device}, generator on {d}")
+            B, S = batch.num_frames, batch.num_sweeps
+            dt = store.upload_tables(batch.tables)               # one copy, on the store's copy stream
+            dv = {name: dt[o:o + n * (8 if t == torch.float64 else 4)].view(t) for name, t, o, n in batch.layout}
+            dv["rel_tf"], dv["ego_T"] = dv["rel_tf"].view(B * S, 16), dv["ego_T"].view(B, 9)
             dv["points4"] = store.columns
-            dv["sweep_start"] = batch.sweep_start.to(d, non_blocking=True)
             store.ready(torch.cuda.current_stream(d))
-        else:
-            dv["points4"] = batch.points4.to(d, non_blocking=True)
-        return dv
+            return dv
+        return {"sweep_offsets": batch.sweep_offsets.to(d, non_blocking=True), "rel_tf": batch.rel_tf.to(d, non_blocking=True),
+                "ego_T": batch.ego_T.to(d, non_blocking=True), "points4": batch.points4.to(d, non_blocking=True)}
 
     def generate(self, batch: FrameBatch, aug: Optional[Sequence[_aug.AugParams]] = None, *, dev: Optional[dict] = None,
                  with_map: bool = True, out_lidar: Optional[torch.Tensor] = None,

@@ -175,6 +175,18 @@ class SweepStore:
                 raise KeyError(f"sweep {k!r} named by this batch is no longer resident in the store (evicted after the batch's "
                                "first generate call); pack the batch again")
 
+    def upload_tables(self, tables: torch.Tensor) -> torch.Tensor:
+        """A batch's per-frame tables (one pinned buffer, ``StoreBatch.tables``) -> device, on the store's copy stream like the
+        sweeps themselves: the compute stream carries no copies at all, only the wait that ``ready`` inserts.  (Four small
+        copies on the compute stream cost a sliding-window step 0.1 ms of idle GPU between its kernels.)"""
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            dt = tables.to(self.device, non_blocking=True)
+        dt.record_stream(main)
+        self._dirty = True
+        self._pending_sources.append(tables)
+        return dt
+
     def ready(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """``stream`` (default: current) waits for every upload issued so far."""
         if self._dirty:
@@ -231,6 +243,8 @@ class StoreBatch:
     max_sweep_points: int
     total_points: int
     keys: tuple = ()                 # distinct sweeps named (pinned in the store until the batch is generated or dropped)
+    tables: Optional[torch.Tensor] = None    # the four arrays above as ONE pinned uint8 buffer (they are views of it): one copy
+    layout: tuple = ()               # (name, dtype, byte offset, elements) of each view inside ``tables``
     rows: dict = dataclasses.field(default_factory=dict)     # key -> (first row, points) at pack time (SweepStore.check_resident)
     _finalizer: object = None
 
@@ -280,12 +294,23 @@ class StoreBatch:
         off[1:] = np.cumsum(counts.reshape(-1))
         if off[-1] >= 2 ** 31:
             raise ValueError("more than 2^31 points in one batch")
-        pin = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if torch.cuda.is_available() else \
-              (lambda a: torch.from_numpy(np.ascontiguousarray(a)))
+        # one pinned buffer for the four tables (float64 ones first: every view stays aligned), uploaded with one copy
+        parts = [("rel_tf", rel.reshape(-1), torch.float64), ("ego_T", ego.reshape(-1), torch.float64),
+                 ("sweep_start", start.reshape(-1), torch.int32), ("sweep_offsets", off.astype(np.int32), torch.int32)]
+        nbytes = sum(a.nbytes for _, a, _ in parts)
+        tables = torch.empty(max(nbytes, 8), dtype=torch.uint8)
+        if torch.cuda.is_available():
+            tables = tables.pin_memory()
+        h, o, layout, views = tables.numpy(), 0, [], {}
+        for name, a, dt in parts:
+            h[o:o + a.nbytes] = np.ascontiguousarray(a).view(np.uint8)
+            views[name] = tables[o:o + a.nbytes].view(dt)
+            layout.append((name, dt, o, a.size))
+            o += a.nbytes
         ids = np.full(B, -1, np.int64) if map_ids is None else np.asarray(map_ids, np.int64)
         keys = tuple({k for f in frames for k in f.keys if k is not None})
-        batch = StoreBatch(store, pin(start.reshape(-1)), pin(off.astype(np.int32)), pin(rel.reshape(B * S, 16)), pin(ego.reshape(B, 9)),
-                           ids, B, S, int(counts.max()) if B else 0, int(off[-1]), keys, {k: store.rows(k) for k in keys})
+        batch = StoreBatch(store, views["sweep_start"], views["sweep_offsets"], views["rel_tf"].reshape(B * S, 16), views["ego_T"].reshape(B, 9),
+                           ids, B, S, int(counts.max()) if B else 0, int(off[-1]), keys, tables, tuple(layout), {k: store.rows(k) for k in keys})
         store._pin(keys)
         batch._finalizer = weakref.finalize(batch, store._unpin, keys)
         return batch
