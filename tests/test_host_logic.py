@@ -258,3 +258,33 @@ def test_uint8_intensities_fit_the_four_byte_bin_record():
     assert int(w.astype(np.uint64).max()) < 1 << 32
     assert np.array_equal(w & np.uint32(8191), np.full(256, cell)) and np.array_equal((w >> np.uint32(13)) << np.uint32(16), bits)
     assert (np.diff(bits.astype(np.int64)) > 0).all()                # unsigned order of the bits == order of the values
+
+
+def test_store_batch_tables_are_one_aligned_buffer(bg):
+    """StoreBatch.pack (host only): the four per-frame tables are views of ONE buffer (one upload), float64 views 8-byte
+    aligned, contents as the separate arrays would be; missing sweeps are empty ranges at row 0"""
+    import collections
+    from bevgen_b200.sweep_store import SweepStore, StoreBatch, StoreFrame
+    s = SweepStore.__new__(SweepStore)
+    s._entries = collections.OrderedDict({("L", 0): (0, 11), ("L", 1): (16, 5), ("L", 2): (24, 0)})
+    s._pins = collections.Counter()
+    poses = bg.synthetic._poses(3)
+    frames = [StoreFrame([("L", 0), None, ("L", 1)], poses, poses[2]), StoreFrame([("L", 2), ("L", 1)], poses[:2], poses[1])]
+    b = StoreBatch.pack(s, frames, 4, map_ids=[0, 1])
+    assert b.tables.dtype.is_floating_point is False and b.tables.numel() == b.h2d_bytes
+    for name, dt, off, n in b.layout:
+        v = getattr(b, name).reshape(-1)
+        assert v.data_ptr() == b.tables.data_ptr() + off and v.numel() == n and off % v.element_size() == 0, name
+    assert b.sweep_start.tolist() == [0, 0, 16, 0, 24, 16, 0, 0]
+    assert b.sweep_offsets.tolist() == [0, 11, 11, 16, 16, 16, 21, 21, 21]
+    assert b.total_points == 21 and b.max_sweep_points == 11 and set(b.keys) == {("L", 0), ("L", 1), ("L", 2)}
+    want = bg.pose.sweep_rel_transforms(poses[2], poses)
+    assert np.array_equal(b.rel_tf.numpy()[:3].reshape(3, 4, 4), want) and np.array_equal(b.rel_tf.numpy()[3].reshape(4, 4), np.eye(4))
+    assert np.array_equal(b.ego_T.numpy()[1].reshape(3, 3), bg.pose.map_matrix_from_pose(poses[1][0], poses[1][1], poses[1][3:7]))
+    assert s._pins[("L", 1)] == 1                                    # pinned until generated / dropped
+    b._release()
+    assert not s._pins
+    with pytest.raises(IndexError):
+        StoreBatch.pack(s, [StoreFrame([("L", 0)] * 5, np.tile(poses[:1], (5, 1)), poses[0])], 4)
+    with pytest.raises(KeyError):
+        StoreBatch.pack(s, [StoreFrame([("L", 9)], poses[:1], poses[0])], 4)
