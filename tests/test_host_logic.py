@@ -288,3 +288,34 @@ def test_store_batch_tables_are_one_aligned_buffer(bg):
         StoreBatch.pack(s, [StoreFrame([("L", 0)] * 5, np.tile(poses[:1], (5, 1)), poses[0])], 4)
     with pytest.raises(KeyError):
         StoreBatch.pack(s, [StoreFrame([("L", 9)], poses[:1], poses[0])], 4)
+
+
+def test_deferred_points_read_like_the_transformed_array(bg, monkeypatch):
+    """bev_ops.DeferredPoints (what install() makes dataset.transform_points return): shape / len / dtype without any work;
+    every other way of reading it -- np.asarray, indexing, iteration, arithmetic, ndarray attributes -- yields the array
+    transform_points returns, computed once (the CUDA call is stubbed here with the reference formula, utils.py:31-33)"""
+    calls = []
+
+    def ref_transform(points, T):
+        calls.append(1)
+        p = np.asarray(points, np.float64)
+        return (np.asarray(T) @ np.c_[p[:, :3], np.ones(len(p))].T).T[:, :3]
+
+    monkeypatch.setattr(bg.bev_ops, "transform_points", ref_transform)
+    raw = np.asfortranarray(np.random.default_rng(0).uniform(-50, 50, (17, 3)).astype(np.float16))
+    T = np.eye(4); T[:3, 3] = [1.0, -2.0, 0.5]; T[0, 1] = 0.25
+    d = bg.bev_ops.transform_points_deferred(raw, T)
+    assert isinstance(d, bg.bev_ops.DeferredPoints) and d.shape == (17, 3) and len(d) == 17 and d.ndim == 2 and d.dtype == np.float64
+    assert not calls                                                  # nothing computed yet
+    raw_before = raw.copy()
+    raw[:] = 0                                                        # the caller's array may change: the snapshot does not
+    want = ref_transform(raw_before, T); calls.clear()
+    assert np.array_equal(np.asarray(d), want) and np.array_equal(d[3:5, :2], want[3:5, :2])
+    assert np.array_equal(d * 2.0, want * 2.0) and np.array_equal(1.0 + d, 1.0 + want) and np.array_equal(-d, -want)
+    assert np.array_equal(d.T, want.T) and d.mean() == want.mean() and np.array_equal(np.stack(list(d)), want)
+    assert np.array_equal(np.asarray(d, dtype=np.float32), want.astype(np.float32)) and (d == want).all()
+    assert len(calls) == 1                                            # materialised once
+    # inputs that are not float16 / float32 sweeps are transformed right away
+    assert isinstance(bg.bev_ops.transform_points_deferred(raw_before.astype(np.float64), T), np.ndarray)
+    with pytest.raises(ValueError):
+        bg.bev_ops.transform_points_deferred(raw_before, np.eye(3))

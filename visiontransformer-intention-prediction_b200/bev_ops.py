@@ -454,6 +454,30 @@ class DeferredPoints:
     def __getitem__(self, idx):
         return self.materialize()[idx]
 
+    def __iter__(self):
+        return iter(self.materialize())
+
+    def __getattr__(self, name):                 # anything else an ndarray has (.T, .mean(), .astype, ...): the real array's
+        if name.startswith("__") or name in ("raw", "matrix", "_value"):      # (own fields not set yet: copy / pickle protocols)
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+
+def _forward_operator(name):
+    def op(self, *args):
+        return getattr(self.materialize(), name)(*args)
+    op.__name__ = name
+    return op
+
+
+for _name in ("add", "sub", "mul", "truediv", "floordiv", "mod", "pow", "matmul", "lt", "le", "gt", "ge", "eq", "ne"):
+    for _dunder in (f"__{_name}__", f"__r{_name}__"):
+        if hasattr(np.ndarray, _dunder):
+            setattr(DeferredPoints, _dunder, _forward_operator(_dunder))
+for _dunder in ("__neg__", "__abs__"):
+    setattr(DeferredPoints, _dunder, _forward_operator(_dunder))
+DeferredPoints.__hash__ = None                   # like ndarray: == is element-wise
+
 
 def transform_points_deferred(points: np.ndarray, transform_matrix: np.ndarray):
     """``transform_points`` for the one place the reference calls it (dataset.py:340, whose results only feed
